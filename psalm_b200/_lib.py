@@ -1,0 +1,86 @@
+"""ctypes binding of libpsalm_b200.so (the C ABI declared in include/psalm_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, we raise.  (The reference
+silently falls back to a slow PyTorch path on *any* exception — ops/modules/ms_deform_attn.py:117 —
+which is exactly what this package must never do.)
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsalm_b200.so")
+
+F32, F16, BF16 = 0, 1, 2
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+class PsalmKernelError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_c_vp, _c_i, _c_i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)
+
+# name -> argtypes; every symbol declared in include/psalm_b200.h must be listed here
+# (tests/test_abi.py cross-checks this table against the header).
+SIGNATURES = {
+    "psalm_abi_version": ([], _c_i),
+    "psalm_last_error": ([], ctypes.c_char_p),
+    "psalm_compiled_arch": ([], _c_i),
+    "psalm_msda_forward": ([_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_i] * 11 + [_c_vp], _c_i),
+    "psalm_msda_encoder_fused": ([_c_vp, _c_vp, _c_vp, _c_i64p, _c_i64p] + [_c_i] * 8 + [_c_vp], _c_i),
+}
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PsalmKernelError(
+            "psalm_b200: %s not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `python psalm_b200/build.py`). There is no CPU / PyTorch fallback." % LIB_PATH)
+    h = ctypes.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(h, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = h
+    return h
+
+
+def dtype_code(t):
+    try:
+        return _DT[t]
+    except KeyError:
+        raise PsalmKernelError("psalm_b200: unsupported dtype %s" % t)
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().psalm_last_error()
+        raise PsalmKernelError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PsalmKernelError("psalm_b200 kernels need CUDA tensors; got a %s tensor. "
+                                   "There is no CPU implementation." % t.device)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def i64_array(vals):
+    arr = (ctypes.c_int64 * len(vals))(*[int(v) for v in vals])
+    return arr
