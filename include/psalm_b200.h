@@ -14,6 +14,7 @@
 #ifndef PSALM_B200_H_
 #define PSALM_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -78,6 +79,57 @@ int psalm_msda_encoder_fused(const void* value, const void* ow, void* out,
                              const int64_t* shapes_host, const int64_t* starts_host,
                              int B, int S, int M, int D, int L, int P,
                              int value_dtype, int ow_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Swin windowed multi-head self-attention (W-MSA / SW-MSA), fused.
+ * Replaces: WindowAttention.forward + the roll / pad / window_partition / window_reverse copies of
+ *   SwinTransformerBlock.forward (multimodal_encoder/swin_trans.py:117-149, 207-245) and the shift
+ *   mask of BasicLayer.forward (swin_trans.py:370-387).
+ *   qkv      [B, H*W, 3*C]  output of the qkv Linear on norm1(x), UNPADDED and UNSHIFTED token order
+ *   qkv_bias [3*C]          value of a zero-padded token after the Linear (swin_trans.py:207-214)
+ *   rel_bias [nh, ws*ws, ws*ws] fp32, relative_position_bias_table gathered by relative_position_index
+ *   out      [B, H*W, C]    attention output before `proj`, original token order (padding cropped)
+ * ------------------------------------------------------------------------------------------ */
+int psalm_window_attention(const void* qkv, const void* qkv_bias, const float* rel_bias, void* out,
+                           int B, int H, int W, int C, int nh, int ws, int shift, int dtype, void* stream);
+
+/* Causal prefill attention of the LLM (third-party PhiAttention eager path; call site
+ * language_model/llava_phi.py:1354-1363).  qkv [B,T,3,nh,hd] with rotary already applied
+ * (psalm_rotary_inplace); key_valid [B,T] uint8 (attention_mask) or NULL; out [B,T,nh*hd].
+ * fp32 softmax as in the reference. */
+int psalm_causal_attention(const void* qkv, const uint8_t* key_valid, void* out, int B, int T, int nh,
+                           int hd, int dtype, void* stream);
+
+/* Partial rotary embedding in place on q and k of qkv [B,T,3,nh,hd]; cos/sin [T, rd/2] fp32
+ * (PhiRotaryEmbedding + apply_rotary_pos_emb on the first rd dims). */
+int psalm_rotary_inplace(void* qkv, const float* cos_t, const float* sin_t, int B, int T, int nh, int hd,
+                         int rd, int dtype, void* stream);
+
+/* Masked cross-attention / query self-attention of the Mask2Former decoder.
+ * Replaces nn.MultiheadAttention's core in CrossAttentionLayer / SelfAttentionLayer
+ *   (transformer_decoder/mask2former_transformer_decoder.py:93-105, 35-45) after the in-projections.
+ *   q [B,Lq,nh*hd], k,v [B,Lk,nh*hd], out [B,Lq,nh*hd]
+ *   mask_bits [B,Lq,ceil(Lk/32)] uint32, bit = 1 -> key blocked (identical for all heads), or NULL
+ *   row_open  [B,Lq] uint8, 1 -> every key of the row is blocked -> the row attends everywhere
+ *             (mask2former_transformer_decoder.py:647), or NULL
+ *   splits > 1 -> split-K over the keys; workspace of psalm_cross_attention_workspace_bytes(). */
+size_t psalm_cross_attention_workspace_bytes(int B, int nh, int hd, int Lq, int splits);
+int psalm_cross_attention(const void* q, const void* k, const void* v, const uint32_t* mask_bits,
+                          const uint8_t* row_open, void* out, float* workspace, int B, int Lq, int Lk,
+                          int nh, int hd, int splits, int dtype, void* stream);
+
+/* Prediction head pieces (mask2former_transformer_decoder.py:695-762).
+ *   psalm_mask_logits: out[b,q,p] = sum_c mask_embed[b,q,c] * feats[b,p,c]
+ *       (= einsum("bqc,bchw->bqhw") at :750 with the feature map stored token-major [B,HW,C])
+ *   psalm_bilinear_tokens: F.interpolate(bilinear, align_corners=False) on token-major maps
+ *       [B,Hi,Wi,C] -> [B,Ho,Wo,C]; accumulate != 0 adds into `out` (FPN top-down add, msdeformattn.py:306)
+ *   psalm_attn_mask_bits: bits = (logit < 0)  (== sigmoid < 0.5, :757-759), row_open = all blocked */
+int psalm_mask_logits(const void* mask_embed, const void* feats, void* out, int B, int Q, int P, int C,
+                      int dtype, int out_dtype, void* stream);
+int psalm_bilinear_tokens(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int dtype,
+                          int out_dtype, int accumulate, void* stream);
+int psalm_attn_mask_bits(const void* logits, uint32_t* bits, uint8_t* row_open, int rows, int P, int dtype,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -124,6 +124,26 @@ msda_vec_kernel(const TV* __restrict__ value, const TL* __restrict__ loc, const 
 #pragma unroll
   for (int i = 0; i < CH; ++i) acc[i] = 0.f;
 
+  // sampling locations / weights of this (query, head): 16-byte loads, every lane of the group
+  // reads the same addresses (broadcast), 9 requests instead of 24 for (L,P) = (3,4)
+  constexpr int LPT = LT * PT;
+  constexpr bool kPreload = (LPT > 0) && (LPT % 4 == 0) && (sizeof(TL) == 4);
+  float plx[kPreload ? LPT : 1], ply[kPreload ? LPT : 1], paw[kPreload ? LPT : 1];
+  if constexpr (kPreload) {
+    const float4* l4 = reinterpret_cast<const float4*>(locp);
+    const float4* w4 = reinterpret_cast<const float4*>(wp);
+#pragma unroll
+    for (int i = 0; i < LPT / 2; ++i) {
+      const float4 v = __ldg(l4 + i);
+      plx[2 * i] = v.x; ply[2 * i] = v.y; plx[2 * i + 1] = v.z; ply[2 * i + 1] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < LPT / 4; ++i) {
+      const float4 v = __ldg(w4 + i);
+      paw[4 * i] = v.x; paw[4 * i + 1] = v.y; paw[4 * i + 2] = v.z; paw[4 * i + 3] = v.w;
+    }
+  }
+
 #pragma unroll
   for (int l = 0; l < (LT ? LT : kMaxLevels); ++l) {
     if (!LT && l >= L) break;
@@ -143,7 +163,9 @@ msda_vec_kernel(const TV* __restrict__ value, const TL* __restrict__ loc, const 
       if (!PT && p >= P) break;
       const int s = l * P + p;
       float lx, ly, aw;
-      if constexpr (sizeof(TL) == 4) {
+      if constexpr (kPreload) {
+        lx = plx[s]; ly = ply[s]; aw = paw[s];
+      } else if constexpr (sizeof(TL) == 4) {
         const float2 xy = __ldg(reinterpret_cast<const float2*>(locp) + s);
         lx = xy.x;
         ly = xy.y;
@@ -233,14 +255,44 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
   const TO* __restrict__ offp = ow + row + (size_t)m * LP * 2;
   const TO* __restrict__ lgp = ow + row + (size_t)M * LP * 2 + (size_t)m * LP;
 
+  // raw offsets (2*LP values) and logits (LP values) of this (query, head), vector loads
+  float offv[2 * LP], lg[LP];
+  if constexpr (sizeof(TO) == 4) {
+    const float4* o4 = reinterpret_cast<const float4*>(offp);
+#pragma unroll
+    for (int i = 0; i < LP / 2; ++i) {
+      const float4 v = __ldg(o4 + i);
+      offv[4 * i] = v.x; offv[4 * i + 1] = v.y; offv[4 * i + 2] = v.z; offv[4 * i + 3] = v.w;
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(lgp);
+#pragma unroll
+    for (int i = 0; i < LP / 4; ++i) {
+      const float4 v = __ldg(g4 + i);
+      lg[4 * i] = v.x; lg[4 * i + 1] = v.y; lg[4 * i + 2] = v.z; lg[4 * i + 3] = v.w;
+    }
+  } else {
+    // 16-bit rows: offsets are 2*LP*2 B (16-byte multiples for LP % 4 == 0), logits LP*2 B (8-byte)
+    const uint4* o4 = reinterpret_cast<const uint4*>(offp);
+#pragma unroll
+    for (int i = 0; i < LP / 4; ++i) {
+      const uint4 v = __ldg(o4 + i);
+      unpack2<TO>(v.x, offv[8 * i], offv[8 * i + 1]);
+      unpack2<TO>(v.y, offv[8 * i + 2], offv[8 * i + 3]);
+      unpack2<TO>(v.z, offv[8 * i + 4], offv[8 * i + 5]);
+      unpack2<TO>(v.w, offv[8 * i + 6], offv[8 * i + 7]);
+    }
+    const uint2* g2 = reinterpret_cast<const uint2*>(lgp);
+#pragma unroll
+    for (int i = 0; i < LP / 4; ++i) {
+      const uint2 v = __ldg(g2 + i);
+      unpack2<TO>(v.x, lg[4 * i], lg[4 * i + 1]);
+      unpack2<TO>(v.y, lg[4 * i + 2], lg[4 * i + 3]);
+    }
+  }
   // softmax over the L*P logits of this (query, head)  (F.softmax, ms_deform_attn.py:105)
-  float lg[LP];
   float mx = -INFINITY;
 #pragma unroll
-  for (int s = 0; s < LP; ++s) {
-    lg[s] = to_f32<TO>(lgp[s]);
-    mx = fmaxf(mx, lg[s]);
-  }
+  for (int s = 0; s < LP; ++s) mx = fmaxf(mx, lg[s]);
   float sum = 0.f;
 #pragma unroll
   for (int s = 0; s < LP; ++s) {
@@ -265,7 +317,7 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
 #pragma unroll
     for (int p = 0; p < PT; ++p) {
       const int s = l * PT + p;
-      const float ox = to_f32<TO>(offp[2 * s]), oy = to_f32<TO>(offp[2 * s + 1]);
+      const float ox = offv[2 * s], oy = offv[2 * s + 1];
       // sampling_locations = ref + off / (W_l, H_l)  (ms_deform_attn.py:109-110), then the
       // kernel-side  w_im = loc_w * W - 0.5  (ms_deform_im2col_cuda.cuh:290-291)
       const float x = (rx + ox / (float)W) * (float)W - 0.5f;

@@ -1,0 +1,145 @@
+"""Torch-tensor wrappers over the C ABI (include/psalm_b200.h).  PyTorch is used only for device
+memory, streams and library GEMMs; every function here launches hand-written sm_100a kernels and
+raises (never falls back) when the library is missing or an argument is wrong."""
+import torch
+
+from . import _lib
+from .msda import ms_deform_attn_forward, msda_encoder_fused  # noqa: F401  (re-exported)
+
+_LAUNCHES = [0]  # kernels launched through this module (bench.py's gpu_launches counter)
+
+
+def launches():
+    return _LAUNCHES[0]
+
+
+def _count(n=1):
+    _LAUNCHES[0] += n
+
+
+def _chk(t, name):
+    if not t.is_cuda:
+        raise _lib.PsalmKernelError("%s: expected a CUDA tensor, got %s (no CPU path)" % (name, t.device))
+    if not t.is_contiguous():
+        raise _lib.PsalmKernelError("%s: tensor must be contiguous" % name)
+
+
+def window_attention(qkv, qkv_bias, rel_bias, B, H, W, C, nh, ws, shift):
+    """qkv [B,H*W,3C] -> attention output [B,H*W,C] (before proj).  swin_trans.py:117-149,194-253."""
+    for t, n in ((qkv, "qkv"), (qkv_bias, "qkv_bias"), (rel_bias, "rel_bias")):
+        _chk(t, "window_attention." + n)
+    if rel_bias.dtype != torch.float32 or tuple(rel_bias.shape) != (nh, ws * ws, ws * ws):
+        raise _lib.PsalmKernelError("window_attention: rel_bias must be fp32 [nh, ws^2, ws^2]")
+    if qkv_bias.dtype != qkv.dtype or tuple(qkv.shape) != (B, H * W, 3 * C):
+        raise _lib.PsalmKernelError("window_attention: bad qkv / bias")
+    out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
+    rc = _lib.lib().psalm_window_attention(_lib.ptr(qkv), _lib.ptr(qkv_bias), _lib.ptr(rel_bias), _lib.ptr(out),
+                                           B, H, W, C, nh, ws, shift, _lib.dtype_code(qkv.dtype),
+                                           _lib.stream_ptr(qkv.device))
+    _lib.check(rc, "psalm_window_attention")
+    _count()
+    return out
+
+
+def rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd):
+    _chk(qkv, "rotary.qkv")
+    _chk(cos, "rotary.cos")
+    _chk(sin, "rotary.sin")
+    rc = _lib.lib().psalm_rotary_inplace(_lib.ptr(qkv), _lib.ptr(cos), _lib.ptr(sin), B, T, nh, hd, rd,
+                                         _lib.dtype_code(qkv.dtype), _lib.stream_ptr(qkv.device))
+    _lib.check(rc, "psalm_rotary_inplace")
+    _count()
+
+
+def causal_attention(qkv, key_valid, B, T, nh, hd):
+    """qkv [B,T,3,nh,hd] (rotary applied) -> [B,T,nh*hd]; key_valid uint8 [B,T] or None."""
+    _chk(qkv, "causal_attention.qkv")
+    if key_valid is not None:
+        _chk(key_valid, "causal_attention.key_valid")
+        if key_valid.dtype != torch.uint8:
+            raise _lib.PsalmKernelError("causal_attention: key_valid must be uint8")
+    out = torch.empty((B, T, nh * hd), dtype=qkv.dtype, device=qkv.device)
+    rc = _lib.lib().psalm_causal_attention(_lib.ptr(qkv), _lib.ptr(key_valid) if key_valid is not None else None,
+                                           _lib.ptr(out), B, T, nh, hd, _lib.dtype_code(qkv.dtype),
+                                           _lib.stream_ptr(qkv.device))
+    _lib.check(rc, "psalm_causal_attention")
+    _count()
+    return out
+
+
+def pick_splits(B, nh, Lq, Lk):
+    """Split-K factor so that a 100-query problem still fills ~2 waves of 148 SMs."""
+    ctas = B * nh * ((Lq + 31) // 32)
+    want = max(1, (2 * 148 + ctas - 1) // ctas)
+    return int(max(1, min(want, (Lk + 255) // 256)))
+
+
+def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, workspace=None):
+    """q [B,Lq,C], k/v [B,Lk,C] (already projected) -> [B,Lq,C]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, "cross_attention." + n)
+    B, Lq, C = q.shape
+    Lk = k.shape[1]
+    hd = C // nh
+    if splits is None:
+        splits = pick_splits(B, nh, Lq, Lk)
+    if splits > 1:
+        need = _lib.lib().psalm_cross_attention_workspace_bytes(B, nh, hd, Lq, splits)
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(need // 4, dtype=torch.float32, device=q.device)
+    out = torch.empty_like(q)
+    rc = _lib.lib().psalm_cross_attention(
+        _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(mask_bits) if mask_bits is not None else None,
+        _lib.ptr(row_open) if row_open is not None else None, _lib.ptr(out),
+        _lib.ptr(workspace) if splits > 1 else None, B, Lq, Lk, nh, hd, splits, _lib.dtype_code(q.dtype),
+        _lib.stream_ptr(q.device))
+    _lib.check(rc, "psalm_cross_attention")
+    _count(2 if splits > 1 else 1)
+    return out
+
+
+def mask_logits(mask_embed, feats, out_dtype=None):
+    """mask_embed [B,Q,C], feats [B,P,C] (token-major) -> [B,Q,P]."""
+    _chk(mask_embed, "mask_logits.mask_embed")
+    _chk(feats, "mask_logits.feats")
+    B, Q, C = mask_embed.shape
+    P = feats.shape[1]
+    out_dtype = out_dtype or mask_embed.dtype
+    out = torch.empty((B, Q, P), dtype=out_dtype, device=feats.device)
+    rc = _lib.lib().psalm_mask_logits(_lib.ptr(mask_embed), _lib.ptr(feats), _lib.ptr(out), B, Q, P, C,
+                                      _lib.dtype_code(feats.dtype), _lib.dtype_code(out_dtype),
+                                      _lib.stream_ptr(feats.device))
+    _lib.check(rc, "psalm_mask_logits")
+    _count()
+    return out
+
+
+def bilinear_tokens(x, Hi, Wi, Ho, Wo, out=None, out_dtype=None, accumulate=False):
+    """x [B,Hi*Wi,C] token-major -> [B,Ho*Wo,C]; F.interpolate(bilinear, align_corners=False) semantics."""
+    _chk(x, "bilinear_tokens.x")
+    B, _, C = x.shape
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        if accumulate:
+            raise _lib.PsalmKernelError("bilinear_tokens: accumulate needs an output tensor")
+        out = torch.empty((B, Ho * Wo, C), dtype=out_dtype, device=x.device)
+    _chk(out, "bilinear_tokens.out")
+    rc = _lib.lib().psalm_bilinear_tokens(_lib.ptr(x), _lib.ptr(out), B, Hi, Wi, Ho, Wo, C, _lib.dtype_code(x.dtype),
+                                          _lib.dtype_code(out.dtype), 1 if accumulate else 0,
+                                          _lib.stream_ptr(x.device))
+    _lib.check(rc, "psalm_bilinear_tokens")
+    _count()
+    return out
+
+
+def attn_mask_bits(logits):
+    """logits [B,Q,P] -> (bits uint32 [B,Q,ceil(P/32)] (as int32 tensor), row_open uint8 [B,Q])."""
+    _chk(logits, "attn_mask_bits.logits")
+    B, Q, P = logits.shape
+    bits = torch.empty((B, Q, (P + 31) // 32), dtype=torch.int32, device=logits.device)
+    row_open = torch.empty((B, Q), dtype=torch.uint8, device=logits.device)
+    rc = _lib.lib().psalm_attn_mask_bits(_lib.ptr(logits), _lib.ptr(bits), _lib.ptr(row_open), B * Q, P,
+                                         _lib.dtype_code(logits.dtype), _lib.stream_ptr(logits.device))
+    _lib.check(rc, "psalm_attn_mask_bits")
+    _count()
+    return bits, row_open

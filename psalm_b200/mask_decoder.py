@@ -1,0 +1,143 @@
+"""Masked-attention transformer decoder + prediction heads, batch-first, token-major.
+
+Mirrors `MultiScaleMaskedTransformerDecoderForOPTPreTrain.forward_woconcat`
+(reference transformer_decoder/mask2former_transformer_decoder.py:596-693) and
+`forward_prediction_heads` (:695-762).  B200-first differences:
+  * masked cross-attention and the 100x100 query self-attention are one fused kernel each
+    (psalm_cross_attention) working on a PACKED BIT mask (1 bit / key, shared by the 8 heads) instead of
+    nn.MultiheadAttention with a float -inf mask of shape [B*8, 100, HW] and materialised probabilities;
+  * the 9 intermediate prediction heads only feed the next attention mask (:668-680; aux outputs are
+    unused at inference, llava_phi.py:1395-1398).  Bilinear interpolation and the mask einsum are both
+    linear, so  interp(einsum(mask_embed, F)) == einsum(mask_embed, interp(F)):  we interpolate
+    mask_features to the three target sizes ONCE per image and each intermediate head is a
+    [100 x 256] x [256 x HW_l] projection + sign test, instead of ten full-resolution einsums of which
+    nine are thresholded and thrown away (236 MB of logits per image in the reference);
+  * `(sigmoid(x) < 0.5)` is `x < 0`; fully blocked rows are opened by a per-row flag (:647).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import kernels
+from .layout import MaskConfig
+from .pixel_decoder import position_embedding_sine_tokens
+
+
+class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
+    def __init__(self, sd, prefix="predictor.", cfg=MaskConfig(), dtype=torch.bfloat16, device="cuda"):
+        self.cfg, self.dtype, self.device = cfg, dtype, device
+        cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
+        g = lambda k: sd[prefix + k]  # noqa: E731
+        w = {}
+        H = cfg.hidden
+        for i in range(cfg.dec_layers):
+            for kind, attn, tag in (("cross", "multihead_attn", "x"), ("self", "self_attn", "s")):
+                p = "transformer_%s_attention_layers.%d." % (kind, i)
+                W, b = g(p + attn + ".in_proj_weight"), g(p + attn + ".in_proj_bias")
+                for j, n in enumerate("qkv"):
+                    w["%s%d.%s.w" % (tag, i, n)] = cv(W[j * H:(j + 1) * H])
+                    w["%s%d.%s.b" % (tag, i, n)] = cv(b[j * H:(j + 1) * H])
+                if tag == "s":  # q and k share the input (tgt + query_pos): one GEMM
+                    w["s%d.qk.w" % i], w["s%d.qk.b" % i] = cv(W[:2 * H]), cv(b[:2 * H])
+                w["%s%d.o.w" % (tag, i)], w["%s%d.o.b" % (tag, i)] = cv(g(p + attn + ".out_proj.weight")), cv(g(p + attn + ".out_proj.bias"))
+                w["%s%d.n.w" % (tag, i)], w["%s%d.n.b" % (tag, i)] = cv(g(p + "norm.weight")), cv(g(p + "norm.bias"))
+            p = "transformer_ffn_layers.%d." % i
+            for n in ("linear1", "linear2", "norm"):
+                w["f%d.%s.w" % (i, n)], w["f%d.%s.b" % (i, n)] = cv(g(p + n + ".weight")), cv(g(p + n + ".bias"))
+        w["dn.w"], w["dn.b"] = cv(g("decoder_norm.weight")), cv(g("decoder_norm.bias"))
+        self.query_embed = cv(g("query_embed.weight"))      # forward_woconcat uses query_embed (:619)
+        self.level_embed = cv(g("level_embed.weight"))
+        for name, n in (("mask_embed", 3), ("SEG_proj", 2), ("CLASS_proj", 2)):
+            for j in range(n):
+                w["%s.%d.w" % (name, j)] = cv(g("%s.layers.%d.weight" % (name, j)))
+                w["%s.%d.b" % (name, j)] = cv(g("%s.layers.%d.bias" % (name, j)))
+        self.w = w
+
+    def _mlp(self, name, n, x):
+        for j in range(n):
+            x = F.linear(x, self.w["%s.%d.w" % (name, j)], self.w["%s.%d.b" % (name, j)])
+            if j < n - 1:
+                x = F.relu(x)
+        return x
+
+    def _heads_common(self, output):
+        dec = F.layer_norm(output, (self.cfg.hidden,), self.w["dn.w"], self.w["dn.b"])
+        return dec, self._mlp("mask_embed", 3, dec)
+
+    # reference-surface entry: NCHW maps in, dict out (mask2former_transformer_decoder.py:488,684-692)
+    def __call__(self, x, mask_features, mask=None, seg_query=None, SEG_embedding=None, class_name_embedding=None,
+                 region_embedding_list=None):
+        if region_embedding_list is not None:
+            raise NotImplementedError("region prompts are outside this build's scope")
+        sizes = [tuple(t.shape[-2:]) for t in x]
+        toks = [t.permute(0, 2, 3, 1).reshape(t.shape[0], -1, t.shape[1]).to(self.dtype).contiguous() for t in x]
+        B, C, H4, W4 = mask_features.shape
+        mf = mask_features.permute(0, 2, 3, 1).reshape(B, H4 * W4, C).to(self.dtype).contiguous()
+        out = self.forward_tokens(toks, sizes, mf, (H4, W4), seg_query, SEG_embedding, class_name_embedding)
+        out["pred_masks"] = out["pred_masks"].view(B, -1, H4, W4)
+        out["pred_region_logits"] = None
+        out["aux_outputs"] = []
+        return out
+
+    def forward_tokens(self, ms_tokens, ms_sizes, mask_features, mf_size, seg_query, SEG_embedding=None,
+                       class_name_embedding=None, return_trace=False):
+        """ms_tokens: 3 maps [B,HW_l,256] (32^2,64^2,128^2 levels); mask_features [B,H4*W4,256];
+        seg_query [B,Q,256].  Returns dict(pred_masks [B,Q,H4*W4], pred_class_name_logits, pred_SEG_logits)."""
+        cfg, w = self.cfg, self.w
+        B, Q, Hd = seg_query.shape
+        nh = cfg.nheads
+        H4, W4 = mf_size
+        srcs, kins = [], []
+        for i in range(3):  # (:607-614); input_proj is the identity (in_channels == hidden_dim, :475-479)
+            Hl, Wl = ms_sizes[i]
+            pos = position_embedding_sine_tokens(Hl, Wl, self.device).to(self.dtype)
+            src = ms_tokens[i] + self.level_embed[i]
+            srcs.append(src)
+            kins.append(src + pos)
+        # attention-mask sources: mask_features interpolated once to each target size (see module docstring)
+        pooled = [kernels.bilinear_tokens(mask_features, H4, W4, hl, wl) for hl, wl in ms_sizes]
+        qpos = self.query_embed.unsqueeze(0)
+        output = seg_query.to(self.dtype)
+        trace = []
+
+        def mask_for(level, out_):
+            _, me = self._heads_common(out_)
+            lg = kernels.mask_logits(me.contiguous(), pooled[level], out_dtype=torch.float32)
+            bits, row_open = kernels.attn_mask_bits(lg)
+            if return_trace:
+                trace.append(lg)
+            return bits, row_open
+
+        bits, row_open = mask_for(0, output)
+        for i in range(cfg.dec_layers):
+            li = i % 3
+            # masked cross-attention (:93-105): q = tgt + query_pos, k = memory + pos, v = memory
+            q = F.linear(output + qpos, w["x%d.q.w" % i], w["x%d.q.b" % i])
+            k = F.linear(kins[li], w["x%d.k.w" % i], w["x%d.k.b" % i])
+            v = F.linear(srcs[li], w["x%d.v.w" % i], w["x%d.v.b" % i])
+            a = kernels.cross_attention(q, k, v, bits, row_open, nh)
+            output = F.layer_norm(output + F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]), (Hd,),
+                                  w["x%d.n.w" % i], w["x%d.n.b" % i])
+            # query self-attention (:35-45): q = k = tgt + query_pos, v = tgt
+            qk = F.linear(output + qpos, w["s%d.qk.w" % i], w["s%d.qk.b" % i])
+            v = F.linear(output, w["s%d.v.w" % i], w["s%d.v.b" % i])
+            a = kernels.cross_attention(qk[..., :Hd].contiguous(), qk[..., Hd:].contiguous(), v, None, None, nh, splits=1)
+            output = F.layer_norm(output + F.linear(a, w["s%d.o.w" % i], w["s%d.o.b" % i]), (Hd,),
+                                  w["s%d.n.w" % i], w["s%d.n.b" % i])
+            # FFN (:158-162)
+            f = F.linear(F.relu(F.linear(output, w["f%d.linear1.w" % i], w["f%d.linear1.b" % i])),
+                         w["f%d.linear2.w" % i], w["f%d.linear2.b" % i])
+            output = F.layer_norm(output + f, (Hd,), w["f%d.norm.w" % i], w["f%d.norm.b" % i])
+            if i < cfg.dec_layers - 1:
+                bits, row_open = mask_for((i + 1) % 3, output)
+        # final prediction heads (:695-750) — the only ones whose outputs leave the decoder
+        dec, me = self._heads_common(output)
+        out = dict(pred_SEG_logits=None, pred_class_name_logits=None)
+        if SEG_embedding is not None:
+            out["pred_SEG_logits"] = torch.bmm(self._mlp("SEG_proj", 2, dec), SEG_embedding.to(self.dtype).transpose(1, 2))
+        if class_name_embedding is not None:
+            out["pred_class_name_logits"] = torch.bmm(self._mlp("CLASS_proj", 2, dec),
+                                                      class_name_embedding.to(self.dtype).transpose(1, 2))
+        out["pred_masks"] = kernels.mask_logits(me.contiguous(), mask_features)
+        if return_trace:
+            out["trace_pooled_logits"] = trace
+        return out

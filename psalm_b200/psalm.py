@@ -1,0 +1,192 @@
+"""`PSALM` — the drop-in object for the reference's segmentation inference path.
+
+Keeps the operator surface of `PSALM(PhiForCausalLM, LlavaMetaForCausalLM)` that the eval scripts use
+(reference language_model/llava_phi.py:146, psalm/model/llava_arch.py:49-63):
+    model.eval_seg(input_ids=..., attention_mask=..., images=..., seg_info=..., class_name_ids=...,
+                   cls_indices=..., class_name_embedding_indices=..., token_refer_id=...,
+                   refer_embedding_indices=..., is_thing_list=...)      -> list[dict]   (llava_phi.py:1317)
+    model.get_model(), model.get_vision_tower(), model.encode_images(images),
+    model.get_vision_tower_feature(images), model.pixel_decoder.forward_features(dict),
+    model.predictor(x, mask_features, None, seg_query, SEG_embedding, class_name_embedding, None)
+and loads the reference checkpoint layout unchanged (layout.py / loader.py).
+
+How it differs from the reference on purpose (results are unchanged):
+  * Swin runs ONCE per image (the reference runs it twice on identical input, llava_phi.py:449 and :223);
+  * every image of the batch is post-processed (the reference returns inside the loop, llava_phi.py:1472);
+  * no CPU / PyTorch fallback for the hot operators: a missing CUDA library raises.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import postprocess as PP
+from . import sequence as SEQ
+from .layout import PsalmConfig
+from .mask_decoder import MultiScaleMaskedTransformerDecoderForOPTPreTrain
+from .phi import PhiModel
+from .pixel_decoder import MSDeformAttnPixelDecoder
+from .projector import ResNetSwin
+from .swin import SwinTransformer
+
+
+class PSALMModel:
+    """`model.model` of the reference (PSALMModel(LlavaMetaModel, PhiModel), llava_phi.py:52): owns the
+    LLM, the vision tower and the projector."""
+
+    def __init__(self, sd, cfg, dtype, device):
+        self.phi = PhiModel(sd, "model.", cfg.phi, dtype, device)
+        self.embed_tokens = self.phi.embed_tokens
+        self.vision_tower = SwinTransformer(sd, "model.vision_tower.", cfg.swin, dtype, device)
+        self.mm_projector = ResNetSwin(sd, "model.mm_projector.", dtype, device)
+
+    def get_vision_tower(self):
+        return self.vision_tower
+
+    def __call__(self, inputs_embeds=None, attention_mask=None, **_):
+        return self.phi(inputs_embeds, attention_mask)
+
+
+class PSALM:
+    def __init__(self, state_dict, cfg: PsalmConfig = PsalmConfig(), dtype=torch.bfloat16, device="cuda",
+                 seg_task="panoptic"):
+        self._check_runtime(device)
+        if dtype == torch.float32:  # true fp32 for parity runs (cuDNN would otherwise pick TF32)
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        self.cfg, self.dtype, self.device = cfg, dtype, torch.device(device)
+        sd = state_dict
+        cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
+        self.model = PSALMModel(sd, cfg, dtype, device)
+        self.pixel_decoder = MSDeformAttnPixelDecoder(sd, "pixel_decoder.", cfg.mask, dtype, device)
+        self.predictor = MultiScaleMaskedTransformerDecoderForOPTPreTrain(sd, "predictor.", cfg.mask, dtype, device)
+        self.seg_query = cv(sd["seg_query"])
+        self.proj = {n: (cv(sd[n + ".weight"]), cv(sd[n + ".bias"]))
+                     for n in ("seg_query_projector", "SEG_token_projector", "class_name_projector")}
+        self.num_queries = cfg.mask.num_queries
+        self.test_topk_per_image = cfg.mask.num_queries
+        self.size_divisibility = cfg.mask.size_divisibility
+        self.set_task(seg_task)
+
+    @staticmethod
+    def _check_runtime(device):
+        """No CPU path and no silent fallback: refuse to construct without a GPU and the built kernels."""
+        if torch.device(device).type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("psalm_b200.PSALM needs a CUDA device: there is no CPU implementation of the hot path")
+        from . import _lib
+        _lib.lib()
+
+    # ---- configuration (llava_phi.py:268-301) ----------------------------------------------------
+    def set_task(self, seg_task):
+        if seg_task not in ("semantic", "instance", "panoptic", "referring"):
+            raise NotImplementedError("SEG_TASK %r (region / video variants are outside this build's scope)" % seg_task)
+        self.seg_task = seg_task
+        self.semantic_on = seg_task in ("semantic", "panoptic")
+        self.instance_on = seg_task in ("instance", "panoptic")
+        self.panoptic_on = seg_task == "panoptic"
+        self.referring_on = seg_task == "referring"
+        self.sem_seg_postprocess_before_inference = self.instance_on or self.panoptic_on or self.referring_on
+
+    @classmethod
+    def from_state_dict(cls, sd, **kw):
+        return cls(sd, **kw)
+
+    # ---- LlavaMetaForCausalLM surface --------------------------------------------------------------
+    def get_model(self):
+        return self.model
+
+    def get_vision_tower(self):
+        return self.model.get_vision_tower()
+
+    def encode_images(self, images):
+        """llava_phi.py:448-451."""
+        feats = self.get_vision_tower()(images)
+        return self.model.mm_projector(feats[-1])
+
+    def get_vision_tower_feature(self, images):
+        """llava_phi.py:222-230."""
+        f = self.get_vision_tower()(images)
+        return dict(res2=f[0], res3=f[1], res4=f[2], res5=f[3])
+
+    # ---- the hot path -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_core(self, images, plan):
+        """Device-only part of eval_seg: images [B,3,H,W] on device, `plan` a SequencePlan on device.
+        Returns dict(pred_masks [B,Q,H4*W4], mask_size, pred_class_name_logits, pred_SEG_logits)."""
+        toks, sizes = self.model.vision_tower.forward_tokens(images)                 # Swin, once
+        h5, w5 = sizes[3]
+        res5 = toks[3].view(toks[3].shape[0], h5, w5, -1).permute(0, 3, 1, 2)
+        img_tok = self.model.mm_projector(res5)                                        # [B,n_img,hidden]
+        embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query)
+        hidden = self.model.phi(embeds, plan.attention_mask if plan.any_padding else None)
+        seg_q = F.linear(SEQ.gather_seg_query(plan, hidden), *self.proj["seg_query_projector"])
+        SEG_emb = cls_emb = None
+        if plan.refer_pool is not None:
+            SEG_emb = F.linear(SEQ.pool(plan.refer_pool, hidden), *self.proj["SEG_token_projector"])
+        if plan.cls_pool is not None:
+            cls_emb = F.linear(SEQ.pool(plan.cls_pool, hidden), *self.proj["class_name_projector"])
+        mask_features, ms, ms_sizes = self.pixel_decoder.forward_tokens(toks, sizes)
+        out = self.predictor.forward_tokens(ms, ms_sizes, mask_features, sizes[0], seg_q, SEG_emb, cls_emb)
+        out["mask_size"] = sizes[0]
+        return out
+
+    def make_plan(self, input_ids, attention_mask, image_hw, class_name_ids=None, cls_indices=None,
+                  class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None):
+        H, W = image_hw
+        ps = self.cfg.swin.patch
+        h, w = -(-H // ps), -(-W // ps)
+        for _ in range(len(self.cfg.swin.depths) - 1):
+            h, w = (h + 1) // 2, (w + 1) // 2
+        n_img = ((h - 1) // 2 + 1) * ((w - 1) // 2 + 1)   # conv3x3 stride 2 pad 1 of the projector
+        return SEQ.build_plan(input_ids, attention_mask, n_img, self.num_queries, class_name_ids, cls_indices,
+                              class_name_embedding_indices, token_refer_id, refer_embedding_indices)
+
+    @torch.no_grad()
+    def eval_seg(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
+                 use_cache=None, output_attentions=None, output_hidden_states=None, images=None, return_dict=None,
+                 seg_info=None, class_name_ids=None, class_name_embedding_indices=None, cls_indices=None,
+                 token_refer_id=None, refer_embedding_indices=None, is_thing_list=None):
+        if self.panoptic_on:
+            assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
+            self.is_thing_list = is_thing_list
+        images_d = images.to(self.device, non_blocking=True)
+        plan = self.make_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
+                              class_name_embedding_indices, token_refer_id, refer_embedding_indices).to(self.device)
+        out = self.forward_core(images_d, plan)
+        return self.post_process(out, images.shape[-2:], seg_info)
+
+    @torch.no_grad()
+    def post_process(self, out, image_hw, seg_info):
+        """llava_phi.py:1395-1472 for EVERY image of the batch."""
+        Hi, Wi = image_hw
+        d = self.size_divisibility
+        Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d     # ImageList.from_tensors(images, 32), :1400
+        H4, W4 = out["mask_size"]
+        B, Q = out["pred_masks"].shape[:2]
+        pm = out["pred_masks"].view(B, Q, H4, W4)
+        mask_pred = F.interpolate(pm.float(), size=(Hp, Wp), mode="bilinear", align_corners=False)
+        results = []
+        for b in range(B):
+            info = seg_info[b]
+            height, width = info.get("height", Hi), info.get("width", Wi)
+            oh, ow = PP.unpadded_box(info["padding_mask"])
+            mp = mask_pred[b]
+            r = {}
+            if self.sem_seg_postprocess_before_inference:
+                mp = PP.sem_seg_postprocess(mp, (oh, ow), height, width)
+            cls = out["pred_class_name_logits"][b].float() if out["pred_class_name_logits"] is not None else None
+            if self.semantic_on:
+                sem = PP.semantic_inference(cls, mp)
+                if not self.sem_seg_postprocess_before_inference:
+                    sem = PP.sem_seg_postprocess(sem, (oh, ow), height, width)
+                r["sem_seg"] = sem
+            if self.instance_on:
+                r["instances"] = PP.instance_inference(cls, mp, self.test_topk_per_image,
+                                                       getattr(self, "is_thing_list", None), self.panoptic_on)
+            if self.panoptic_on:
+                r["panoptic_seg"] = PP.panoptic_inference(cls, mp, self.is_thing_list,
+                                                          self.cfg.mask.object_mask_threshold,
+                                                          self.cfg.mask.overlap_threshold)
+            if self.referring_on:
+                r["instances"] = PP.seg_instance_inference(out["pred_SEG_logits"][b].float(), mp,
+                                                           self.test_topk_per_image)
+            results.append(r)
+        return results

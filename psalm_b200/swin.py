@@ -1,0 +1,99 @@
+"""Swin-B vision tower, token-major, for the PSALM hot path.
+
+Mirrors `SwinTransformer.forward` (reference psalm/model/multimodal_encoder/swin_trans.py:608-633):
+four stage outputs (strides 4/8/16/32), each through its own LayerNorm.  Differences in *how*:
+  * activations stay token-major [B, H*W, C]; the NCHW tuple the reference returns is a strided view;
+  * W-MSA / SW-MSA is ONE fused kernel per block (psalm_window_attention): cyclic shift, window
+    partition, the zero padding after norm1 (swin_trans.py:207-214), the relative-position bias gather
+    (:131-134) and the -100 shift mask (:370-387) are folded into the kernel's addressing, so the
+    reference's roll / pad / partition / reverse copies do not exist;
+  * the relative-position bias is gathered once at weight-preparation time into a dense fp32 table.
+Linear layers are library GEMMs (cuBLAS through torch)."""
+import torch
+import torch.nn.functional as F
+
+from . import kernels
+from .layout import SwinConfig
+
+
+class SwinTransformer:
+    def __init__(self, sd, prefix="model.vision_tower.", cfg=SwinConfig(), dtype=torch.bfloat16, device="cuda"):
+        self.cfg, self.dtype, self.device = cfg, dtype, device
+        self.image_processor = {}
+        self.num_features = [cfg.embed_dim * 2 ** i for i in range(len(cfg.depths))]
+        g = lambda k: sd[prefix + k]  # noqa: E731
+        cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
+        w = {}
+        w["pe.w"] = cv(g("patch_embed.proj.weight")).contiguous(memory_format=torch.channels_last)
+        w["pe.b"] = cv(g("patch_embed.proj.bias"))
+        w["pe.nw"], w["pe.nb"] = cv(g("patch_embed.norm.weight")), cv(g("patch_embed.norm.bias"))
+        ws = cfg.window
+        for s, depth in enumerate(cfg.depths):
+            nh = cfg.num_heads[s]
+            for b in range(depth):
+                p = "layers.%d.blocks.%d." % (s, b)
+                for n in ("norm1", "norm2", "attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2"):
+                    w[p + n + ".w"] = cv(g(p + n + ".weight"))
+                    w[p + n + ".b"] = cv(g(p + n + ".bias"))
+                idx = g(p + "attn.relative_position_index").view(-1).long()
+                tab = g(p + "attn.relative_position_bias_table").float()
+                # [ws^2*ws^2, nh] -> [nh, ws^2, ws^2] fp32 (swin_trans.py:131-134)
+                w[p + "rel"] = tab[idx].view(ws * ws, ws * ws, nh).permute(2, 0, 1).contiguous().to(device)
+            if s < len(cfg.depths) - 1:
+                p = "layers.%d.downsample." % s
+                w[p + "red.w"] = cv(g(p + "reduction.weight"))
+                w[p + "norm.w"], w[p + "norm.b"] = cv(g(p + "norm.weight")), cv(g(p + "norm.bias"))
+            w["norm%d.w" % s], w["norm%d.b" % s] = cv(g("norm%d.weight" % s)), cv(g("norm%d.bias" % s))
+        self.w = w
+
+    # -- public surface of the reference -----------------------------------------------------------
+    def __call__(self, images):
+        return self.forward(images)
+
+    def forward(self, images):
+        """images [B,3,H,W] -> tuple of 4 NCHW maps (strided views of the token-major results)."""
+        toks, sizes = self.forward_tokens(images)
+        return tuple(t.view(t.shape[0], h, w_, t.shape[2]).permute(0, 3, 1, 2) for t, (h, w_) in zip(toks, sizes))
+
+    # -- token-major pipeline ----------------------------------------------------------------------
+    def forward_tokens(self, images):
+        cfg, w = self.cfg, self.w
+        x = images.to(device=self.device, dtype=self.dtype)
+        _, _, H, W = x.shape
+        ps = cfg.patch
+        if W % ps != 0:  # swin_trans.py:431-434
+            x = F.pad(x, (0, ps - W % ps))
+        if H % ps != 0:
+            x = F.pad(x, (0, 0, 0, ps - H % ps))
+        x = F.conv2d(x.contiguous(memory_format=torch.channels_last), w["pe.w"], w["pe.b"], stride=ps)
+        B, C, Wh, Ww = x.shape
+        x = x.permute(0, 2, 3, 1).reshape(B, Wh * Ww, C)
+        x = F.layer_norm(x, (C,), w["pe.nw"], w["pe.nb"])
+        outs, sizes = [], []
+        ws = cfg.window
+        for s, depth in enumerate(cfg.depths):
+            nh = cfg.num_heads[s]
+            for b in range(depth):
+                p = "layers.%d.blocks.%d." % (s, b)
+                shift = 0 if b % 2 == 0 else ws // 2
+                h = F.layer_norm(x, (C,), w[p + "norm1.w"], w[p + "norm1.b"])
+                qkv = F.linear(h, w[p + "attn.qkv.w"], w[p + "attn.qkv.b"])
+                a = kernels.window_attention(qkv, w[p + "attn.qkv.b"], w[p + "rel"], B, Wh, Ww, C, nh, ws, shift)
+                x = x + F.linear(a, w[p + "attn.proj.w"], w[p + "attn.proj.b"])
+                h = F.layer_norm(x, (C,), w[p + "norm2.w"], w[p + "norm2.b"])
+                h = F.gelu(F.linear(h, w[p + "mlp.fc1.w"], w[p + "mlp.fc1.b"]))
+                x = x + F.linear(h, w[p + "mlp.fc2.w"], w[p + "mlp.fc2.b"])
+            outs.append(F.layer_norm(x, (C,), w["norm%d.w" % s], w["norm%d.b" % s]))
+            sizes.append((Wh, Ww))
+            if s < len(cfg.depths) - 1:  # PatchMerging swin_trans.py:269-296
+                p = "layers.%d.downsample." % s
+                xm = x.view(B, Wh, Ww, C)
+                if Wh % 2 == 1 or Ww % 2 == 1:
+                    xm = F.pad(xm, (0, 0, 0, Ww % 2, 0, Wh % 2))
+                xm = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1)
+                Wh, Ww = (Wh + 1) // 2, (Ww + 1) // 2
+                xm = xm.reshape(B, Wh * Ww, 4 * C)
+                xm = F.layer_norm(xm, (4 * C,), w[p + "norm.w"], w[p + "norm.b"])
+                x = F.linear(xm, w[p + "red.w"])
+                C = 2 * C
+        return outs, sizes

@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE — CPU emulation of the CUDA entry points in psalm_b200.kernels, built from
+plain torch ops, so the *host orchestration* (weight preparation, layouts, sequence plans, decoder
+control flow, post-processing) can be checked against the oracle on a machine without a GPU.
+It lives under tests/ and is installed by monkeypatching inside tests only; the product has no such
+switch and refuses to run without CUDA (tests/test_abi.py::test_no_cpu_path)."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import psalm_oracle as O
+
+
+def window_attention(qkv, qkv_bias, rel_bias, B, H, W, C, nh, ws, shift):
+    hd = C // nh
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    x = qkv_bias.view(1, 1, 1, 3 * C).expand(B, Hp, Wp, 3 * C).clone()
+    x[:, :H, :W] = qkv.view(B, H, W, 3 * C)
+    if shift:
+        x = torch.roll(x, (-shift, -shift), (1, 2))
+    xw = O._window_partition(x, ws).view(-1, ws * ws, 3, nh, hd).permute(2, 0, 3, 1, 4).float()
+    q, k, v = xw[0], xw[1], xw[2]
+    attn = (q @ k.transpose(-2, -1)) * hd ** -0.5 + rel_bias.unsqueeze(0)
+    if shift:
+        m = O._shift_mask(H, W, ws, shift)
+        nW = m.shape[0]
+        attn = (attn.view(B, nW, nh, ws * ws, ws * ws) + m.unsqueeze(1).unsqueeze(0)).view(-1, nh, ws * ws, ws * ws)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, ws, ws, C)
+    o = O._window_reverse(o, ws, Hp, Wp)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o[:, :H, :W].reshape(B, H * W, C).to(qkv.dtype)
+
+
+def rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd):
+    half = rd // 2
+    for which in (0, 1):
+        x = qkv[:, :, which].float()
+        x1, x2 = x[..., :half].clone(), x[..., half:rd].clone()
+        c, s = cos[None, :, None, :], sin[None, :, None, :]
+        qkv[:, :, which, :, :half] = (x1 * c - x2 * s).to(qkv.dtype)
+        qkv[:, :, which, :, half:rd] = (x2 * c + x1 * s).to(qkv.dtype)
+
+
+def causal_attention(qkv, key_valid, B, T, nh, hd):
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).float() for i in range(3))
+    s = (q @ k.transpose(-2, -1)) * hd ** -0.5
+    allowed = torch.tril(torch.ones(T, T, dtype=torch.bool))[None, None]
+    if key_valid is not None:
+        allowed = allowed & key_valid.bool()[:, None, None, :]
+    s = s.masked_fill(~allowed, float("-inf"))
+    p = torch.nan_to_num(s.softmax(-1))
+    return (p @ v).permute(0, 2, 1, 3).reshape(B, T, nh * hd).to(qkv.dtype)
+
+
+def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, workspace=None):
+    B, Lq, C = q.shape
+    Lk = k.shape[1]
+    hd = C // nh
+    qh, kh, vh = (t.view(B, -1, nh, hd).permute(0, 2, 1, 3).float() for t in (q, k, v))
+    s = (qh @ kh.transpose(-2, -1)) / math.sqrt(hd)
+    if mask_bits is not None:
+        w = mask_bits.long() & 0xFFFFFFFF
+        bit = (w.unsqueeze(-1) >> torch.arange(32)) & 1
+        blocked = bit.view(B, Lq, -1)[..., :Lk].bool()
+        if row_open is not None:
+            blocked = blocked & ~row_open.bool().unsqueeze(-1)
+        s = s.masked_fill(blocked.unsqueeze(1), float("-inf"))
+    return (s.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B, Lq, C).to(q.dtype)
+
+
+def mask_logits(mask_embed, feats, out_dtype=None):
+    return torch.bmm(mask_embed.float(), feats.float().transpose(1, 2)).to(out_dtype or mask_embed.dtype)
+
+
+def bilinear_tokens(x, Hi, Wi, Ho, Wo, out=None, out_dtype=None, accumulate=False):
+    B, _, C = x.shape
+    y = F.interpolate(x.float().view(B, Hi, Wi, C).permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear",
+                      align_corners=False).permute(0, 2, 3, 1).reshape(B, Ho * Wo, C)
+    if out is None:
+        return y.to(out_dtype or x.dtype)
+    out.copy_((out.float() + y if accumulate else y).to(out.dtype))
+    return out
+
+
+def attn_mask_bits(logits):
+    B, Q, P = logits.shape
+    W32 = (P + 31) // 32
+    blocked = torch.zeros(B, Q, W32 * 32, dtype=torch.int64)
+    blocked[..., :P] = (logits.float() < 0).long()
+    words = (blocked.view(B, Q, W32, 32) << torch.arange(32)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    row_open = (logits.float() < 0).all(-1).to(torch.uint8)
+    return words, row_open
+
+
+def msda_encoder_fused(value_hm, ow, spatial_shapes, level_start_index, n_points=4):
+    B, M, S, D = value_hm.shape
+    L = len(spatial_shapes)
+    LP = L * n_points
+    off = ow[..., : M * LP * 2].float().view(B, S, M, L, n_points, 2)
+    aw = ow[..., M * LP * 2:].float().view(B, S, M, LP).softmax(-1).view(B, S, M, L, n_points)
+    ref = O.encoder_reference_points(spatial_shapes, B)
+    norm = torch.tensor([[w, h] for h, w in spatial_shapes], dtype=torch.float32)
+    loc = ref[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    return O.msda_core(value_hm.permute(0, 2, 1, 3).float(), spatial_shapes, loc, aw).to(value_hm.dtype)
+
+
+def install(monkeypatch):
+    from psalm_b200 import kernels
+    for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
+                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused"):
+        monkeypatch.setattr(kernels, name, globals()[name])

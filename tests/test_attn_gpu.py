@@ -1,0 +1,113 @@
+"""CUDA attention / prediction-head kernels (through the C ABI) vs independent torch restatements
+(tests/emu.py, fp32 CPU math on the storage-rounded inputs)."""
+import pytest
+import torch
+
+import emu
+from psalm_b200 import kernels
+
+pytestmark = pytest.mark.gpu
+DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+TOL = {"f32": 2e-5, "f16": 2e-3, "bf16": 1.2e-2}   # max |err| / max |ref|; 16-bit = output rounding
+
+
+def _close(out, ref, dt, scale=1.0):
+    out, ref = out.float().cpu(), ref.float().cpu()
+    err = (out - ref).abs().max() / (ref.abs().max() + 1e-30)
+    assert err < TOL[dt] * scale, "rel-to-max error %.3e (tol %.1e)" % (err, TOL[dt] * scale)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("H,W,shift", [(24, 24, 0), (24, 36, 6), (17, 29, 6), (50, 13, 6), (7, 5, 0)])
+def test_window_attention(dt, H, W, shift):
+    torch.manual_seed(H * 100 + W + shift)
+    B, C, nh, ws = 2, 64, 2, 12
+    qkv = torch.randn(B, H * W, 3 * C).to(DT[dt])
+    bias = (torch.randn(3 * C) * 0.5).to(DT[dt])
+    rel = torch.randn(nh, ws * ws, ws * ws)
+    ref = emu.window_attention(qkv.float(), bias.float(), rel, B, H, W, C, nh, ws, shift)
+    out = kernels.window_attention(qkv.cuda(), bias.cuda(), rel.cuda(), B, H, W, C, nh, ws, shift)
+    _close(out, ref, dt)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("T,padded", [(77, False), (130, True), (33, True)])
+def test_rotary_and_causal_attention(dt, T, padded):
+    torch.manual_seed(T)
+    B, nh, hd, rd = 2, 4, 64, 32
+    qkv = torch.randn(B, T, 3, nh, hd).to(DT[dt])
+    inv = 1.0 / (10000.0 ** (torch.arange(0, rd, 2).float() / rd))
+    fr = torch.arange(T).float()[:, None] * inv[None]
+    cos, sin = fr.cos().contiguous(), fr.sin().contiguous()
+    kv = None
+    if padded:
+        kv = torch.ones(B, T, dtype=torch.uint8)
+        kv[1, T - 9:] = 0
+    ref_qkv = qkv.float().clone()
+    emu.rotary_inplace(ref_qkv, cos, sin, B, T, nh, hd, rd)
+    g = qkv.cuda()
+    kernels.rotary_inplace(g, cos.cuda(), sin.cuda(), B, T, nh, hd, rd)
+    _close(g, ref_qkv, dt)
+    ref = emu.causal_attention(g.float().cpu(), kv, B, T, nh, hd)
+    out = kernels.causal_attention(g, kv.cuda() if kv is not None else None, B, T, nh, hd)
+    _close(out, ref, dt)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("Lq,Lk,splits", [(100, 1024, None), (100, 4096, 4), (100, 389, 3), (37, 100, 1), (100, 100, 1)])
+def test_cross_attention_with_bit_mask(dt, Lq, Lk, splits):
+    torch.manual_seed(Lq + Lk)
+    B, nh, hd = 2, 8, 32
+    C = nh * hd
+    q, k, v = (torch.randn(B, n, C).to(DT[dt]) for n in (Lq, Lk, Lk))
+    logits = torch.randn(B, Lq, Lk)
+    logits[0, 3] = -1.0          # fully blocked row -> must attend everywhere (DEC:647)
+    logits[1, 0] = 1.0           # fully open row
+    bits, row_open = emu.attn_mask_bits(logits)
+    assert int(row_open[0, 3]) == 1 and int(row_open[1, 0]) == 0
+    ref = emu.cross_attention(q.float(), k.float(), v.float(), bits, row_open, nh)
+    out = kernels.cross_attention(q.cuda(), k.cuda(), v.cuda(), bits.cuda(), row_open.cuda(), nh, splits=splits)
+    _close(out, ref, dt)
+    ref2 = emu.cross_attention(q.float(), k.float(), v.float(), None, None, nh)
+    out2 = kernels.cross_attention(q.cuda(), k.cuda(), v.cuda(), None, None, nh, splits=splits)
+    _close(out2, ref2, dt)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+def test_mask_head_kernels(dt):
+    torch.manual_seed(0)
+    B, Q, C, H4, W4 = 2, 100, 256, 40, 52
+    me = torch.randn(B, Q, C).to(DT[dt])
+    mf = torch.randn(B, H4 * W4, C).to(DT[dt])
+    ref = emu.mask_logits(me.float(), mf.float(), torch.float32)
+    out = kernels.mask_logits(me.cuda(), mf.cuda(), out_dtype=torch.float32)
+    _close(out, ref, "f32" if dt == "f32" else dt, scale=1.0)
+    out_t = kernels.mask_logits(me.cuda(), mf.cuda())
+    assert out_t.dtype == DT[dt]
+    _close(out_t, ref, dt)
+    for Ho, Wo in ((5, 7), (10, 13), (20, 26), (80, 104)):
+        refb = emu.bilinear_tokens(mf.float(), H4, W4, Ho, Wo)
+        outb = kernels.bilinear_tokens(mf.cuda(), H4, W4, Ho, Wo)
+        _close(outb, refb, dt)
+    lg = torch.randn(B, Q, 389)
+    lg[1, 7] = -2.0
+    bits_ref, ro_ref = emu.attn_mask_bits(lg)
+    bits, ro = kernels.attn_mask_bits(lg.cuda())
+    assert torch.equal(bits.cpu(), bits_ref) and torch.equal(ro.cpu(), ro_ref)
+
+
+def test_pooled_mask_equals_reference_order():
+    """interp(einsum(me, F)) vs einsum(me, interp(F)) (mask_decoder.py docstring): count sign flips of
+    the resulting attention mask at the exact 2x/4x/8x factors and at a non-integer factor."""
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    B, Q, C = 1, 100, 256
+    me = torch.randn(B, Q, C).cuda()
+    for (H4, W4), (Hl, Wl) in (((64, 64), (8, 8)), ((64, 64), (32, 32)), ((50, 66), (7, 9))):
+        mf = torch.randn(B, H4 * W4, C).cuda()
+        full = kernels.mask_logits(me, mf, out_dtype=torch.float32).view(B, Q, H4, W4)
+        ref = F.interpolate(full, size=(Hl, Wl), mode="bilinear", align_corners=False).flatten(2) < 0
+        pooled = kernels.bilinear_tokens(mf, H4, W4, Hl, Wl)
+        got = kernels.mask_logits(me, pooled, out_dtype=torch.float32) < 0
+        flips = (ref != got).float().mean().item()
+        assert flips < 1e-4, flips

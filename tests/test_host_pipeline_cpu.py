@@ -1,0 +1,92 @@
+"""Host logic of the hot path, checked on CPU against the oracle and the reference-generated golden
+fixtures with the CUDA entry points emulated by tests/emu.py (test-only monkeypatch)."""
+import numpy as np
+import pytest
+import torch
+
+import emu
+from oracle import psalm_oracle as O
+from psalm_b200 import sequence as SEQ
+from psalm_b200 import synth
+from psalm_b200.layout import PhiConfig, PsalmConfig
+
+SMALL = PsalmConfig(phi=PhiConfig(hidden=256, layers=2, heads=4, inter=1024))
+SMALL_O = dict(hidden=256, layers=2, heads=4, inter=1024, eps=1e-5, theta=10000.0, rotary_frac=0.5)
+
+
+@pytest.mark.parametrize("task,ragged", [("panoptic", False), ("panoptic", True), ("referring", True)])
+def test_sequence_plan_matches_oracle(task, ragged):
+    """build_plan + materialize_embeds == the reference's per-token splice (oracle.assemble_sequence)."""
+    inp = synth.synth_inputs(batch=3, height=64, width=64, task=task, n_classes=9, seed=4, ragged=ragged)
+    g = torch.Generator().manual_seed(0)
+    C, n_img, n_q = 32, 6, 100
+    sd = {"model.embed_tokens.weight": torch.randn(51200, C, generator=g), "seg_query": torch.randn(n_q, C, generator=g)}
+    img = torch.randn(3, n_img, C, generator=g)
+    ref = O.assemble_sequence(sd, inp["input_ids"], inp["attention_mask"], img, inp.get("class_name_ids"),
+                              inp.get("cls_indices"), inp.get("class_name_embedding_indices"),
+                              inp.get("token_refer_id"), inp.get("refer_embedding_indices"))
+    plan = SEQ.build_plan(inp["input_ids"], inp["attention_mask"], n_img, n_q, inp.get("class_name_ids"),
+                          inp.get("cls_indices"), inp.get("class_name_embedding_indices"),
+                          inp.get("token_refer_id"), inp.get("refer_embedding_indices"))
+    emb = SEQ.materialize_embeds(plan, sd["model.embed_tokens.weight"], img, sd["seg_query"])
+    assert torch.equal(emb, ref["inputs_embeds"])
+    assert torch.equal(plan.attention_mask, ref["attention_mask"])
+    hidden = torch.randn(3, plan.T, C, generator=g)
+    assert torch.equal(SEQ.gather_seg_query(plan, hidden), O.get_seg_query(hidden, ref["seg_query_mask"]))
+    if task == "panoptic":
+        assert torch.allclose(SEQ.pool(plan.cls_pool, hidden),
+                              O.get_class_name_embedding(hidden, ref["class_name_embedding_indices"]), atol=1e-6)
+    else:
+        assert torch.allclose(SEQ.pool(plan.refer_pool, hidden),
+                              O.get_SEG_embedding(hidden, ref["refer_embedding_indices"]), atol=1e-6)
+
+
+def _emu_model(monkeypatch, sd, task):
+    from psalm_b200.psalm import PSALM
+    emu.install(monkeypatch)
+
+    class _EmuPSALM(PSALM):
+        @staticmethod
+        def _check_runtime(device):   # tests only: host-logic check with emulated kernels
+            pass
+    return _EmuPSALM(sd, SMALL, torch.float32, "cpu", task)
+
+
+CASES = [("panoptic", 192, 192, 20, 0, 1, False), ("panoptic", 200, 264, 12, 3, 1, False),
+         ("referring", 192, 192, 0, 5, 1, False), ("panoptic", 96, 128, 7, 7, 2, True)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%dx%d_b%d" % (c[0], c[1], c[2], c[5]))
+def test_host_pipeline_matches_golden(monkeypatch, golden, case):
+    task, H, W, ncls, seed, batch, ragged = case
+    sd = synth.synth_state_dict(SMALL, seed=seed)
+    inp = synth.synth_inputs(batch=batch, height=H, width=W, task=task, n_classes=ncls, seed=seed + 1, ragged=ragged)
+    m = _emu_model(monkeypatch, sd, task)
+    g = golden("e2e_%s_%dx%d_b%d.npz" % (task, H, W, batch))
+    plan = m.make_plan(inp["input_ids"], inp["attention_mask"], (H, W), inp.get("class_name_ids"), inp.get("cls_indices"),
+                       inp.get("class_name_embedding_indices"), inp.get("token_refer_id"), inp.get("refer_embedding_indices"))
+    out = m.forward_core(inp["images"], plan)
+    H4, W4 = out["mask_size"]
+    pm = out["pred_masks"].view(batch, -1, H4, W4)
+    assert list(pm.shape) == g["pred_masks_shape"].tolist()
+    got = pm.reshape(-1)[torch.from_numpy(g["pred_masks_idx"])].numpy()
+    scale = np.abs(g["pred_masks"]).max()
+    assert np.abs(got - g["pred_masks"]).max() / scale < 2e-3
+    if "pred_class_name_logits" in g:
+        cl = out["pred_class_name_logits"].numpy()
+        assert np.allclose(cl, g["pred_class_name_logits"], rtol=1e-3, atol=2e-3)
+        assert np.array_equal(cl.argmax(-1), g["pred_class_name_logits"].argmax(-1))
+    if "pred_SEG_logits" in g:
+        assert np.allclose(out["pred_SEG_logits"].numpy(), g["pred_SEG_logits"], rtol=1e-3, atol=2e-3)
+    m.is_thing_list = inp.get("is_thing_list")
+    res = m.post_process(out, (H, W), inp["seg_info"])
+    if "panoptic_seg" in g:
+        pan, info = res[0]["panoptic_seg"]
+        assert (pan.numpy() != g["panoptic_seg"]).mean() < 2e-3
+        assert [[d["id"], int(d["isthing"]), d["category_id"]] for d in info] == g["panoptic_info"].tolist()
+        assert np.array_equal(res[0]["sem_seg"].argmax(0).numpy().astype(np.uint8), g["sem_seg_argmax"]) or \
+            (res[0]["sem_seg"].argmax(0).numpy().astype(np.uint8) != g["sem_seg_argmax"]).mean() < 2e-3
+    if "inst_scores_sorted" in g:
+        sc = res[0]["instances"].scores
+        order = torch.argsort(sc, descending=True, stable=True)
+        assert np.allclose(sc[order].numpy(), g["inst_scores_sorted"], rtol=1e-3, atol=1e-4)
