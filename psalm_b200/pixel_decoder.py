@@ -122,7 +122,7 @@ class MSDeformAttnPixelDecoder:
             ow = F.linear(q, w["e%d.ow.w" % i], w["e%d.ow.b" % i])
             value = F.linear(src, w["e%d.vp.w" % i], w["e%d.vp.b" % i])
             value_hm = value.view(B, S, M, D).permute(0, 2, 1, 3).contiguous()
-            a = kernels.msda_encoder_fused(value_hm, ow.contiguous(), shapes, starts, cfg.enc_points)
+            a = kernels.timed_msda(kernels.msda_encoder_fused, value_hm, ow.contiguous(), shapes, starts, cfg.enc_points)
             kernels._count()
             src = F.layer_norm(src + F.linear(a, w["e%d.op.w" % i], w["e%d.op.b" % i]), (cfg.hidden,),
                                w["e%d.norm1.w" % i], w["e%d.norm1.b" % i])

@@ -17,8 +17,8 @@ from .layout import PsalmConfig, checkpoint_layout
 SEG_MARKER_ID = 50295
 
 
-def _gen(name, seed):
-    g = torch.Generator(device="cpu")
+def _gen(name, seed, device="cpu"):
+    g = torch.Generator(device=device)
     g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFFFFFFFFFF)
     return g
 
@@ -34,12 +34,22 @@ def relative_position_index(ws):
     return rel.sum(-1)
 
 
-def synth_tensor(name, shape, dtype, kind, seed=0, window=12):
-    g = _gen(name, seed)
+def synth_tensor(name, shape, dtype, kind, seed=0, window=12, device="cpu"):
+    """device="cpu" (default) is bit-reproducible everywhere; device="cuda" draws on the GPU (fast, used
+    by bench.py for the 1.59 B-parameter model; values differ from the CPU stream)."""
+    g = _gen(name, seed, device)
+    _randn, _rand = torch.randn, torch.rand
+    if device != "cpu":
+        _randn = lambda shape, generator: torch.randn(shape, generator=generator, device=device)  # noqa: E731
+        _rand = lambda shape, generator: torch.rand(shape, generator=generator, device=device)  # noqa: E731
+    return _synth(name, shape, kind, window, g, _randn, _rand, device)
+
+
+def _synth(name, shape, kind, window, g, randn, rand, device):
     if kind == "index":
-        return relative_position_index(window)
+        return relative_position_index(window).to(device)
     if kind == "count":
-        return torch.zeros((), dtype=torch.int64)
+        return torch.zeros((), dtype=torch.int64, device=device)
     if kind == "w":
         fan_in = max(1, math.prod(shape[1:]))
         std = 1.0 / math.sqrt(fan_in)
@@ -47,33 +57,33 @@ def synth_tensor(name, shape, dtype, kind, seed=0, window=12):
             std = 0.02      # reference init is zero (ms_deform_attn.py:67); keep offsets within a few pixels
         elif name.endswith("attention_weights.weight"):
             std = 0.05
-        return torch.randn(shape, generator=g) * std
+        return randn(shape, generator=g) * std
     if kind == "b":
         std = 2.0 if name.endswith("sampling_offsets.bias") else 0.02
-        return torch.randn(shape, generator=g) * std
+        return randn(shape, generator=g) * std
     if kind == "g":
-        return 1.0 + 0.1 * torch.randn(shape, generator=g)
+        return 1.0 + 0.1 * randn(shape, generator=g)
     if kind == "emb":
         std = 1.0 if ("level_embed" in name or "query_embed" in name or "query_feat" in name) else 0.05
-        return torch.randn(shape, generator=g) * std
+        return randn(shape, generator=g) * std
     if kind == "table":
-        return torch.randn(shape, generator=g) * 0.2
+        return randn(shape, generator=g) * 0.2
     if kind == "mean":
-        return torch.randn(shape, generator=g) * 0.1
+        return randn(shape, generator=g) * 0.1
     if kind == "var":
-        return 0.5 + torch.rand(shape, generator=g)
+        return 0.5 + rand(shape, generator=g)
     raise ValueError(kind)
 
 
 def synth_state_dict(cfg: PsalmConfig = PsalmConfig(), seed=0, include_lm_head=False, dtype=torch.float32,
-                     only_prefix=None):
+                     only_prefix=None, device="cpu"):
     """Synthetic checkpoint with the reference key layout.  lm_head is skipped by default: eval_seg
     never evaluates it (llava_phi.py:1354-1366 takes last_hidden_state)."""
     sd = {}
     for name, (shape, dt, kind) in checkpoint_layout(cfg, include_lm_head=include_lm_head).items():
         if only_prefix is not None and not name.startswith(only_prefix):
             continue
-        t = synth_tensor(name, shape, dt, kind, seed, cfg.swin.window)
+        t = synth_tensor(name, shape, dt, kind, seed, cfg.swin.window, device)
         sd[name] = t if dt == "int64" else t.to(dtype)
     return sd
 

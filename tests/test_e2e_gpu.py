@@ -1,0 +1,105 @@
+"""End-to-end parity of psalm_b200.PSALM (CUDA kernels through the C ABI) against the fixtures the
+UNMODIFIED reference produced (tests/golden/e2e_*.npz) and against the oracle, on the GPU.
+
+Tolerances.  north_star: "within 1e-3 rel on mask logits, bit-exact argmax class ids".  We measure
+rel = max|err| / max|ref| on the final mask logits:
+  fp32 run   : < 1e-3   (asserted; typically ~1e-5) and class argmax exactly equal
+  fp16 / bf16: storage rounding accumulates over ~60 layers; asserted < 3e-2 / 8e-2 with the observed
+               values printed (see DESIGN.md "precision"), class-argmax agreement >= 97 % / 90 %."""
+import numpy as np
+import pytest
+import torch
+
+from psalm_b200 import synth
+from psalm_b200.layout import PhiConfig, PsalmConfig
+
+pytestmark = pytest.mark.gpu
+SMALL = PsalmConfig(phi=PhiConfig(hidden=256, layers=2, heads=4, inter=1024))
+CASES = [("panoptic", 192, 192, 20, 0, 1, False), ("panoptic", 200, 264, 12, 3, 1, False),
+         ("referring", 192, 192, 0, 5, 1, False), ("panoptic", 96, 128, 7, 7, 2, True)]
+
+
+def _run(case, dtype):
+    from psalm_b200.psalm import PSALM
+    task, H, W, ncls, seed, batch, ragged = case
+    sd = synth.synth_state_dict(SMALL, seed=seed)
+    inp = synth.synth_inputs(batch=batch, height=H, width=W, task=task, n_classes=ncls, seed=seed + 1, ragged=ragged)
+    m = PSALM(sd, SMALL, dtype, "cuda", task)
+    plan = m.make_plan(inp["input_ids"], inp["attention_mask"], (H, W), inp.get("class_name_ids"), inp.get("cls_indices"),
+                       inp.get("class_name_embedding_indices"), inp.get("token_refer_id"),
+                       inp.get("refer_embedding_indices")).to("cuda")
+    out = m.forward_core(inp["images"].cuda(), plan)
+    kw = {k: inp[k] for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "token_refer_id",
+                              "refer_embedding_indices", "is_thing_list") if k in inp}
+    res = m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                     seg_info=inp["seg_info"], **kw)
+    torch.cuda.synchronize()
+    return out, res
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%dx%d_b%d" % (c[0], c[1], c[2], c[5]))
+def test_fp32_matches_reference_golden(golden, case):
+    task, H, W, ncls, seed, batch, ragged = case
+    g = golden("e2e_%s_%dx%d_b%d.npz" % (task, H, W, batch))
+    out, res = _run(case, torch.float32)
+    pm = out["pred_masks"].float().cpu().reshape(-1)[torch.from_numpy(g["pred_masks_idx"])].numpy()
+    rel = np.abs(pm - g["pred_masks"]).max() / np.abs(g["pred_masks"]).max()
+    print("fp32 mask-logit rel err %.3e" % rel)
+    assert rel < 1e-3
+    if "pred_class_name_logits" in g:
+        cl = out["pred_class_name_logits"].float().cpu().numpy()
+        assert np.array_equal(cl.argmax(-1), g["pred_class_name_logits"].argmax(-1))
+        assert np.allclose(cl, g["pred_class_name_logits"], rtol=1e-3, atol=2e-3)
+    if "pred_SEG_logits" in g:
+        assert np.allclose(out["pred_SEG_logits"].float().cpu().numpy(), g["pred_SEG_logits"], rtol=1e-3, atol=2e-3)
+    if "panoptic_seg" in g:
+        pan, info = res[0]["panoptic_seg"]
+        assert (pan.cpu().numpy() != g["panoptic_seg"]).mean() < 2e-3
+        assert [[d["id"], int(d["isthing"]), d["category_id"]] for d in info] == g["panoptic_info"].tolist()
+        assert (res[0]["sem_seg"].argmax(0).cpu().numpy().astype(np.uint8) != g["sem_seg_argmax"]).mean() < 2e-3
+    if "inst_scores_sorted" in g:
+        sc = res[0]["instances"].scores.cpu()
+        order = torch.argsort(sc, descending=True, stable=True)
+        assert np.allclose(sc[order].numpy(), g["inst_scores_sorted"], rtol=1e-3, atol=1e-4)
+    assert len(res) == batch   # every image is post-processed (the reference stops after image 0)
+
+
+@pytest.mark.parametrize("dtype,tol,agree", [(torch.float16, 3e-2, 0.97), (torch.bfloat16, 8e-2, 0.90)],
+                         ids=["fp16", "bf16"])
+def test_low_precision_tracks_reference(golden, dtype, tol, agree):
+    case = CASES[0]
+    g = golden("e2e_panoptic_192x192_b1.npz")
+    out, res = _run(case, dtype)
+    pm = out["pred_masks"].float().cpu().reshape(-1)[torch.from_numpy(g["pred_masks_idx"])].numpy()
+    rel = np.abs(pm - g["pred_masks"]).max() / np.abs(g["pred_masks"]).max()
+    nrm = np.linalg.norm(pm - g["pred_masks"]) / np.linalg.norm(g["pred_masks"])
+    cl = out["pred_class_name_logits"].float().cpu().numpy()
+    ag = (cl.argmax(-1) == g["pred_class_name_logits"].argmax(-1)).mean()
+    print("%s: mask-logit max-rel %.3e, l2-rel %.3e, class-argmax agreement %.3f" % (dtype, rel, nrm, ag))
+    assert np.isfinite(pm).all() and rel < tol and ag >= agree
+
+
+def test_full_size_bf16_smoke():
+    """The configuration BASELINE.json's metric is quoted on: 1024^2, Swin-B + Phi-1.5, 100 queries,
+    134 class names, bf16.  No oracle at this size in the GPU suite (it takes minutes on CPU):
+    shapes, finiteness, run-to-run determinism and structural invariants of the outputs."""
+    from psalm_b200.psalm import PSALM
+    cfg = PsalmConfig()
+    sd = synth.synth_state_dict(cfg, seed=0, device="cuda")
+    m = PSALM(sd, cfg, torch.bfloat16, "cuda", "panoptic")
+    del sd
+    inp = synth.synth_inputs(batch=1, height=1024, width=1024, task="panoptic", n_classes=134, seed=1)
+    kw = {k: inp[k] for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "is_thing_list")}
+    r1 = m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                    seg_info=inp["seg_info"], **kw)
+    r2 = m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                    seg_info=inp["seg_info"], **kw)
+    torch.cuda.synchronize()
+    sem = r1[0]["sem_seg"]
+    assert tuple(sem.shape) == (133, 1024, 1024) and torch.isfinite(sem).all()
+    pan, info = r1[0]["panoptic_seg"]
+    assert tuple(pan.shape) == (1024, 1024) and pan.dtype == torch.int32
+    assert set(np.unique(pan.cpu().numpy()).tolist()) <= set([0] + [d["id"] for d in info])
+    assert torch.equal(pan, r2[0]["panoptic_seg"][0]) and torch.equal(sem, r2[0]["sem_seg"])
+    inst = r1[0]["instances"]
+    assert inst.pred_masks.shape[1:] == (1024, 1024) and torch.isfinite(inst.scores).all()
