@@ -99,7 +99,9 @@ def cpu_reference_time(n_images=1, threads=None, seed=0):
     from oracle import psalm_oracle as O
     from psalm_b200 import synth
     from psalm_b200.layout import PsalmConfig
-    threads = threads or os.cpu_count()
+    # all host cores the port can use productively: measured on the 128-core box, 16-32 threads are
+    # fastest (9.1 s / image), 64 threads 15.5 s, 128 threads 198 s (oversubscribed small ops)
+    threads = threads or min(32, os.cpu_count())
     torch.set_num_threads(threads)
     sd = synth.synth_state_dict(PsalmConfig(), seed=seed)
     inp = synth.synth_inputs(batch=1, height=IMG, width=IMG, task="panoptic", n_classes=N_CLASSES, seed=1)
@@ -156,7 +158,7 @@ def run_ours(args, rank, world, local_rank):
     cfg = PsalmConfig()
     dtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.dtype]
     sd = synth.synth_state_dict(cfg, seed=0, device=str(dev))
-    model = PSALM(sd, cfg, dtype, dev, "panoptic")
+    model = PSALM(sd, cfg, dtype, dev, "panoptic", use_cuda_graph=not args.no_graph)
     del sd
     torch.cuda.empty_cache()
     inp = synth.synth_inputs(batch=B, height=IMG, width=IMG, task="panoptic", n_classes=N_CLASSES, seed=1 + rank)
@@ -174,7 +176,7 @@ def run_ours(args, rank, world, local_rank):
                              inp["cls_indices"], inp["class_name_embedding_indices"]).to(dev)
 
     def step_device():
-        out = model.forward_core(images_d, plan_d)
+        out = model.forward_core(images_d, plan_d) if args.no_graph else model.forward_core_graphed(images_d, plan_d)
         return model.post_process(out, (IMG, IMG), inp["seg_info"])
 
     for _ in range(W):
@@ -183,8 +185,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    kernels.PROFILE_EVENTS = []          # (start, end) event pairs around every MSDeformAttn launch
-    l0 = kernels.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -194,6 +194,17 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    # roofline leg: the same K steps launched eagerly (a CUDA graph cannot carry timing events), with
+    # CUDA events on the launch stream around every MSDeformAttn launch; also counts our launches per step
+    def step_eager():
+        out = model.forward_core(images_d, plan_d)
+        return model.post_process(out, (IMG, IMG), inp["seg_info"])
+    step_eager()
+    kernels.PROFILE_EVENTS = []
+    l0 = kernels.launches()
+    for _ in range(K):
+        step_eager()
+    torch.cuda.synchronize()
     launches = kernels.launches() - l0
     ev = kernels.PROFILE_EVENTS
     kernels.PROFILE_EVENTS = None
@@ -247,14 +258,16 @@ def run_ours(args, rank, world, local_rank):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "images_per_step": B * world, "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (3.2 GB of weights are streamed every step)",
-                       "timed": "Swin (once) + projector + Phi prefill + pixel decoder + masked decoder + post-processing"},
+                       "timed": "Swin (once) + projector + Phi prefill + pixel decoder + masked decoder + post-processing",
+                       "cuda_graph": not args.no_graph},
             "e2e": {"value": e2e_value, "unit": "masks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "msda_encoder_fused_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
-                         "avg_us": avg_us, "launches_timed": len(msda_us), "algorithmic_bytes_per_launch": alg}}
+                         "avg_us": avg_us, "launches_timed": len(msda_us), "algorithmic_bytes_per_launch": alg,
+                         "timed_in": "K eager steps of the same workload, CUDA events on the launch stream"}}
     if world == 1 and not args.no_cpu_baseline:
         times, threads = cpu_reference_time(1)
         line["cpu_baseline"] = {"value": 100.0 / times[0], "unit": "masks/s", "cores": threads, "kind": "port",
@@ -271,6 +284,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

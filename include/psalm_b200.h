@@ -93,6 +93,10 @@ int psalm_msda_encoder_fused(const void* value, const void* ow, void* out,
 int psalm_window_attention(const void* qkv, const void* qkv_bias, const float* rel_bias, void* out,
                            int B, int H, int W, int C, int nh, int ws, int shift, int dtype, void* stream);
 
+/* Attention implementation selector: 0 = auto (tensor-core kernels for fp16/bf16 storage, fp32 SIMT
+ * kernels for fp32 storage), 1 = force the fp32-math SIMT kernels for every storage type (parity runs). */
+int psalm_set_attention_impl(int impl);
+
 /* Causal prefill attention of the LLM (third-party PhiAttention eager path; call site
  * language_model/llava_phi.py:1354-1363).  qkv [B,T,3,nh,hd] with rotary already applied
  * (psalm_rotary_inplace); key_valid [B,T] uint8 (attention_mask) or NULL; out [B,T,nh*hd].

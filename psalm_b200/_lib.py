@@ -32,6 +32,7 @@ SIGNATURES = {
     "psalm_compiled_arch": ([], _c_i),
     "psalm_msda_forward": ([_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_i] * 11 + [_c_vp], _c_i),
     "psalm_msda_encoder_fused": ([_c_vp, _c_vp, _c_vp, _c_i64p, _c_i64p] + [_c_i] * 8 + [_c_vp], _c_i),
+    "psalm_set_attention_impl": ([_c_i], _c_i),
     "psalm_window_attention": ([_c_vp] * 4 + [_c_i] * 8 + [_c_vp], _c_i),
     "psalm_causal_attention": ([_c_vp] * 3 + [_c_i] * 5 + [_c_vp], _c_i),
     "psalm_rotary_inplace": ([_c_vp] * 3 + [_c_i] * 6 + [_c_vp], _c_i),

@@ -1,0 +1,490 @@
+// Tensor-core attention kernels for 16-bit storage (bf16 / fp16), fp32 accumulate and softmax.
+//
+//   flash_mma_kernel   FlashAttention-2 style: 64 query rows x 64-key tiles per CTA (4 warps), online
+//                      softmax in registers, policies as in attn_simt.cu (causal prefill, masked
+//                      cross-attention with packed bit masks + split-K, plain self-attention).
+//   window_mma_kernel  one CTA per (Swin window, head): the whole 144 x 144 score tile lives in
+//                      registers (9 warps x 16 rows), single-pass softmax, relative-position bias and
+//                      the shift mask applied on the accumulators, window gather / zero padding / cyclic
+//                      shift resolved once per CTA into a token table in shared memory.
+// Both use warp-level mma.sync.m16n8k16 with ldmatrix operand fetch.  (tcgen05 is reserved for the
+// GEMM-shaped mask projection — these tiles are 144- or 64-wide with per-element bias / mask work in
+// the accumulators, which TMEM round trips would not speed up; see DESIGN.md.)
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace psalm {
+
+struct AttnDims {
+  int B, H, Lq, Lk, splits;
+  float scale;
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// policies (raw 16-byte loads = 8 elements; score(); paired stores)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct CausalMma {
+  const T* qkv;              // [B,T,3,nh,hd]
+  const uint8_t* key_valid;  // [B,T] or null
+  T* out;                    // [B,T,nh*hd]
+  int T_, nh, hd;
+  static constexpr bool kCausal = true;
+  __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
+    return ldg16(qkv + (((size_t)b * T_ + n) * 3 + which) * nh * hd + h * hd + d0);
+  }
+  __device__ __forceinline__ float score(int b, int h, int qi, int kj, float s) const {
+    if (kj > qi) return -INFINITY;
+    if (key_valid && !key_valid[(size_t)b * T_ + kj]) return -INFINITY;
+    return s;
+  }
+  __device__ __forceinline__ void store2(int b, int h, int n, int d, float v0, float v1) const {
+    *reinterpret_cast<uint32_t*>(out + ((size_t)b * T_ + n) * nh * hd + h * hd + d) = pack2<T>(v0, v1);
+  }
+  __device__ __forceinline__ void store(int b, int h, int n, int d, float v) const {
+    out[((size_t)b * T_ + n) * nh * hd + h * hd + d] = from_f32<T>(v);
+  }
+};
+
+template <typename T>
+struct CrossMma {
+  const T *q, *k, *v;
+  const uint32_t* bits;
+  const uint8_t* row_open;
+  T* out;
+  int Lq, Lk, nh, hd, W32;
+  static constexpr bool kCausal = false;
+  __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
+    const T* base = which == 0 ? q : (which == 1 ? k : v);
+    const int L = which == 0 ? Lq : Lk;
+    return ldg16(base + ((size_t)b * L + n) * nh * hd + h * hd + d0);
+  }
+  __device__ __forceinline__ float score(int b, int h, int qi, int kj, float s) const {
+    if (bits) {
+      const size_t row = (size_t)b * Lq + qi;
+      if (!(row_open && row_open[row]) && ((__ldg(bits + row * W32 + (kj >> 5)) >> (kj & 31)) & 1u)) return -INFINITY;
+    }
+    return s;
+  }
+  __device__ __forceinline__ void store2(int b, int h, int n, int d, float v0, float v1) const {
+    *reinterpret_cast<uint32_t*>(out + ((size_t)b * Lq + n) * nh * hd + h * hd + d) = pack2<T>(v0, v1);
+  }
+  __device__ __forceinline__ void store(int b, int h, int n, int d, float v) const {
+    out[((size_t)b * Lq + n) * nh * hd + h * hd + d] = from_f32<T>(v);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// flash kernel: grid = (q_tiles * splits, H, B), block = 128 (4 warps x 16 query rows)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int HD, typename Policy>
+__global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm, float* __restrict__ part) {
+  constexpr int BQ = 64, BK = 64, LD = HD + 8;
+  __shared__ __align__(16) T Qs[BQ * LD];
+  __shared__ __align__(16) T Ks[BK * LD];
+  __shared__ __align__(16) T Vs[BK * LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int qt = blockIdx.x / dm.splits, sp = blockIdx.x - qt * dm.splits;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * BQ;
+  const int ktiles = (dm.Lk + BK - 1) / BK;
+  const int tps = (ktiles + dm.splits - 1) / dm.splits;
+  const int kt0 = sp * tps;
+  int kt1 = kt0 + tps < ktiles ? kt0 + tps : ktiles;
+  if (Policy::kCausal) {
+    const int e = (q0 + BQ - 1) / BK + 1;
+    kt1 = e < kt1 ? e : kt1;
+  }
+  // ---- Q tile -> smem -> A fragments in registers
+  for (int i = tid; i < BQ * HD / 8; i += 128) {
+    const int row = i / (HD / 8), d0 = (i % (HD / 8)) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + row < dm.Lq) v = pol.load8(0, b, h, q0 + row, d0);
+    *reinterpret_cast<uint4*>(&Qs[row * LD + d0]) = v;
+  }
+  __syncthreads();
+  uint32_t qa[HD / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks)
+    ldsm_x4(qa[ks], &Qs[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8]);
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const float sc = dm.scale;
+
+  for (int kt = kt0; kt < kt1; ++kt) {
+    __syncthreads();
+    for (int i = tid; i < BK * HD / 8; i += 128) {
+      const int row = i / (HD / 8), d0 = (i % (HD / 8)) * 8;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+      const int kj = kt * BK + row;
+      if (kj < dm.Lk) {
+        kv = pol.load8(1, b, h, kj, d0);
+        vv = pol.load8(2, b, h, kj, d0);
+      }
+      *reinterpret_cast<uint4*>(&Ks[row * LD + d0]) = kv;
+      *reinterpret_cast<uint4*>(&Vs[row * LD + d0]) = vv;
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t kb[4];
+        const int mi = lane >> 3;
+        ldsm_x4(kb, &Ks[(np * 16 + (lane & 7) + (mi >> 1) * 8) * LD + ks * 16 + (mi & 1) * 8]);
+        mma16816<T>(s[2 * np], qa[ks], kb[0], kb[1]);
+        mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+      }
+    }
+    // ---- scale, policy mask, online softmax (log2 domain)
+    float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = (e < 2) ? r0 : r1;
+        const int kj = kt * BK + nt * 8 + 2 * t4 + (e & 1);
+        float v = -INFINITY;
+        if (qi < dm.Lq && kj < dm.Lk) v = pol.score(b, h, qi, kj, s[nt][e] * sc) * kLog2e;
+        s[nt][e] = v;
+        tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+      const float m_new = fmaxf(m_run[r], tmax[r]);
+      corr[r] = (m_new == -INFINITY || m_run[r] == -INFINITY) ? (m_new == -INFINITY ? 1.f : 0.f) : exp2f(m_run[r] - m_new);
+      m_run[r] = m_new;
+    }
+    float psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        const float p = (s[nt][e] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_run[r]);
+        s[nt][e] = p;
+        psum[r] += p;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 1);
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 2);
+      l_run[r] = l_run[r] * corr[r] + psum[r];
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < HD / 16; ++dp) {
+        uint32_t vb[4];
+        const int mi = lane >> 3;
+        ldsm_x4_t(vb, &Vs[(kk * 16 + (lane & 7) + (mi & 1) * 8) * LD + dp * 16 + (mi >> 1) * 8]);
+        mma16816<T>(o[2 * dp], pa, vb[0], vb[1]);
+        mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+  // ---- epilogue
+  if (dm.splits == 1) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = r ? r1 : r0;
+      if (qi >= dm.Lq) continue;
+      const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) pol.store2(b, h, qi, i * 8 + 2 * t4, o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = r ? r1 : r0;
+      if (qi >= dm.Lq) continue;
+      float* pr = part + ((((size_t)b * dm.H + h) * dm.splits + sp) * dm.Lq + qi) * (HD + 2);
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        pr[i * 8 + 2 * t4] = o[i][2 * r];
+        pr[i * 8 + 2 * t4 + 1] = o[i][2 * r + 1];
+      }
+      if (t4 == 0) {
+        pr[HD] = m_run[r];      // log2 domain
+        pr[HD + 1] = l_run[r];
+      }
+    }
+  }
+}
+
+template <typename Policy, int HD>
+__global__ void flash_combine_kernel(Policy pol, AttnDims dm, const float* __restrict__ part) {
+  const long long n = (long long)dm.B * dm.H * dm.Lq * HD;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int d = (int)(t % HD); t /= HD;
+    const int qi = (int)(t % dm.Lq); t /= dm.Lq;
+    const int h = (int)(t % dm.H);
+    const int b = (int)(t / dm.H);
+    const float* base = part + (((size_t)b * dm.H + h) * dm.splits * dm.Lq + qi) * (HD + 2);
+    const size_t stride = (size_t)dm.Lq * (HD + 2);
+    float M = -INFINITY;
+    for (int s = 0; s < dm.splits; ++s) M = fmaxf(M, base[s * stride + HD]);
+    float L = 0.f, O = 0.f;
+    if (M != -INFINITY) {
+      for (int s = 0; s < dm.splits; ++s) {
+        const float ms = base[s * stride + HD];
+        if (ms == -INFINITY) continue;
+        const float e = exp2f(ms - M);
+        L += base[s * stride + HD + 1] * e;
+        O += base[s * stride + d] * e;
+      }
+    }
+    pol.store(b, h, qi, d, L > 0.f ? O / L : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Swin window kernel: grid = (B*nW, nh), block = 288 (9 warps), N = 144 tokens, head_dim 32
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(288) window_mma_kernel(const T* __restrict__ qkv, const T* __restrict__ qkv_bias,
+                                                         const float* __restrict__ rel, T* __restrict__ out,
+                                                         int H, int W, int Hp, int Wp, int shift, int nh, int C,
+                                                         int nWx, int nW) {
+  constexpr int N = 144, WS = 12, HD = 32, LD = HD + 8;
+  __shared__ __align__(16) T Qs[N * LD];
+  __shared__ __align__(16) T Ks[N * LD];
+  __shared__ __align__(16) T Vs[N * LD];
+  __shared__ int tok[N];
+  __shared__ unsigned char reg[N];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int z = blockIdx.x, h = blockIdx.y;
+  if (tid < N) {  // window gather: cyclic shift + zero padding resolved once (swin_trans.py:207-225)
+    const int win = z % nW, bi = z / nW;
+    const int wy = win / nWx, wx = win - wy * nWx;
+    const int i = tid / WS, j = tid - i * WS;
+    const int py = wy * WS + i, px = wx * WS + j;
+    const int rh = py < Hp - WS ? 0 : (py < Hp - shift ? 1 : 2);
+    const int rw = px < Wp - WS ? 0 : (px < Wp - shift ? 1 : 2);
+    reg[tid] = (unsigned char)(rh * 3 + rw);
+    int oy = py + shift, ox = px + shift;
+    if (oy >= Hp) oy -= Hp;
+    if (ox >= Wp) ox -= Wp;
+    tok[tid] = (oy < H && ox < W) ? (bi * H + oy) * W + ox : -1;
+  }
+  __syncthreads();
+  for (int i = tid; i < N * 3 * (HD / 8); i += 288) {
+    const int which = i / (N * (HD / 8));
+    const int rem = i - which * (N * (HD / 8));
+    const int row = rem / (HD / 8), d0 = (rem % (HD / 8)) * 8;
+    const int col = which * C + h * HD + d0;
+    const int tk = tok[row];
+    const uint4 v = tk >= 0 ? ldg16(qkv + (size_t)tk * 3 * C + col) : ldg16(qkv_bias + col);
+    T* dst = which == 0 ? Qs : (which == 1 ? Ks : Vs);
+    *reinterpret_cast<uint4*>(&dst[row * LD + d0]) = v;
+  }
+  __syncthreads();
+  uint32_t qa[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+    ldsm_x4(qa[ks], &Qs[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8]);
+  float s[18][4];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 9; ++np) {
+      uint32_t kb[4];
+      const int mi = lane >> 3;
+      ldsm_x4(kb, &Ks[(np * 16 + (lane & 7) + (mi >> 1) * 8) * LD + ks * 16 + (mi & 1) * 8]);
+      mma16816<T>(s[2 * np], qa[ks], kb[0], kb[1]);
+      mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+    }
+  }
+  const float sc = rsqrtf((float)HD);
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const float* rel0 = rel + ((size_t)h * N + r0) * N;
+  const float* rel1 = rel + ((size_t)h * N + r1) * N;
+  const int reg0 = reg[r0], reg1 = reg[r1];
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 18; ++nt) {
+    const int kj = nt * 8 + 2 * t4;
+    const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
+    const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
+    float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
+    if (shift > 0) {
+      const int ra = reg[kj], rb = reg[kj + 1];
+      m00 = ra != reg0 ? -100.f : 0.f; m01 = rb != reg0 ? -100.f : 0.f;
+      m10 = ra != reg1 ? -100.f : 0.f; m11 = rb != reg1 ? -100.f : 0.f;
+    }
+    s[nt][0] = (s[nt][0] * sc + b0.x + m00) * kLog2e;
+    s[nt][1] = (s[nt][1] * sc + b0.y + m01) * kLog2e;
+    s[nt][2] = (s[nt][2] * sc + b1.x + m10) * kLog2e;
+    s[nt][3] = (s[nt][3] * sc + b1.y + m11) * kLog2e;
+    mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+    mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+#pragma unroll
+  for (int nt = 0; nt < 18; ++nt) {
+    s[nt][0] = exp2f(s[nt][0] - mx[0]); s[nt][1] = exp2f(s[nt][1] - mx[0]);
+    s[nt][2] = exp2f(s[nt][2] - mx[1]); s[nt][3] = exp2f(s[nt][3] - mx[1]);
+    sum[0] += s[nt][0] + s[nt][1];
+    sum[1] += s[nt][2] + s[nt][3];
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+  }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      uint32_t vb[4];
+      const int mi = lane >> 3;
+      ldsm_x4_t(vb, &Vs[(kk * 16 + (lane & 7) + (mi & 1) * 8) * LD + dp * 16 + (mi >> 1) * 8]);
+      mma16816<T>(o[2 * dp], pa, vb[0], vb[1]);
+      mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int tk = tok[r ? r1 : r0];
+    if (tk < 0) continue;  // padded token: cropped (swin_trans.py:244-245)
+    const float inv = 1.f / sum[r];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint32_t*>(out + (size_t)tk * C + h * HD + i * 8 + 2 * t4) =
+          pack2<T>(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers used by the C-ABI entry points in attn_simt.cu
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename Policy>
+static int launch_flash(const Policy& pol, AttnDims dm, int hd, float* workspace, cudaStream_t st, const char* what) {
+  dim3 grid(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
+  PSALM_REQUIRE(dm.H <= 65535 && dm.B <= 65535, "%s: grid too large", what);
+  PSALM_REQUIRE(dm.splits == 1 || workspace != nullptr, "%s: split-K needs a workspace", what);
+  if (hd == 32) {
+    flash_mma_kernel<T, 32, Policy><<<grid, 128, 0, st>>>(pol, dm, workspace);
+    if (dm.splits > 1) flash_combine_kernel<Policy, 32><<<148 * 2, 256, 0, st>>>(pol, dm, workspace);
+  } else if (hd == 64) {
+    flash_mma_kernel<T, 64, Policy><<<grid, 128, 0, st>>>(pol, dm, workspace);
+    if (dm.splits > 1) flash_combine_kernel<Policy, 64><<<148 * 2, 256, 0, st>>>(pol, dm, workspace);
+  } else {
+    set_error("%s: head_dim %d unsupported by the tensor-core path", what, hd);
+    return PSALM_E_UNSUPPORTED;
+  }
+  return check_launch(what);
+}
+
+int mma_causal_attention(const void* qkv, const uint8_t* key_valid, void* out, int B, int T_, int nh, int hd,
+                         int dtype, cudaStream_t st) {
+  AttnDims dm{B, nh, T_, T_, 1, 1.0f / sqrtf((float)hd)};
+  if (dtype == PSALM_BF16) {
+    CausalMma<__nv_bfloat16> pol{(const __nv_bfloat16*)qkv, key_valid, (__nv_bfloat16*)out, T_, nh, hd};
+    return launch_flash<__nv_bfloat16>(pol, dm, hd, nullptr, st, "causal_attention(mma)");
+  }
+  CausalMma<__half> pol{(const __half*)qkv, key_valid, (__half*)out, T_, nh, hd};
+  return launch_flash<__half>(pol, dm, hd, nullptr, st, "causal_attention(mma)");
+}
+
+int mma_cross_attention(const void* q, const void* k, const void* v, const uint32_t* bits, const uint8_t* row_open,
+                        void* out, float* workspace, int B, int Lq, int Lk, int nh, int hd, int splits, int dtype,
+                        cudaStream_t st) {
+  AttnDims dm{B, nh, Lq, Lk, splits, 1.0f / sqrtf((float)hd)};
+  if (dtype == PSALM_BF16) {
+    using T = __nv_bfloat16;
+    CrossMma<T> pol{(const T*)q, (const T*)k, (const T*)v, bits, row_open, (T*)out, Lq, Lk, nh, hd, (Lk + 31) / 32};
+    return launch_flash<T>(pol, dm, hd, workspace, st, "cross_attention(mma)");
+  }
+  using T = __half;
+  CrossMma<T> pol{(const T*)q, (const T*)k, (const T*)v, bits, row_open, (T*)out, Lq, Lk, nh, hd, (Lk + 31) / 32};
+  return launch_flash<T>(pol, dm, hd, workspace, st, "cross_attention(mma)");
+}
+
+int mma_window_attention(const void* qkv, const void* qkv_bias, const float* rel, void* out, int B, int H, int W,
+                         int C, int nh, int shift, int dtype, cudaStream_t st) {
+  const int ws = 12;
+  const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
+  const int nWx = Wp / ws, nW = nWx * (Hp / ws);
+  dim3 grid(B * nW, nh);
+  PSALM_REQUIRE(nh <= 65535, "window_attention: too many heads");
+  if (dtype == PSALM_BF16)
+    window_mma_kernel<__nv_bfloat16><<<grid, 288, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_bias, rel,
+                                                          (__nv_bfloat16*)out, H, W, Hp, Wp, shift, nh, C, nWx, nW);
+  else
+    window_mma_kernel<__half><<<grid, 288, 0, st>>>((const __half*)qkv, (const __half*)qkv_bias, rel, (__half*)out, H,
+                                                   W, Hp, Wp, shift, nh, C, nWx, nW);
+  return check_launch("window_mma_kernel");
+}
+
+}  // namespace psalm

@@ -320,7 +320,23 @@ __global__ void rotary_kernel(T* __restrict__ qkv, const float* __restrict__ cs,
 
 }  // namespace psalm
 
+namespace psalm {
+// tensor-core paths (attn_mma.cu)
+int mma_causal_attention(const void*, const uint8_t*, void*, int, int, int, int, int, cudaStream_t);
+int mma_cross_attention(const void*, const void*, const void*, const uint32_t*, const uint8_t*, void*, float*, int,
+                        int, int, int, int, int, int, cudaStream_t);
+int mma_window_attention(const void*, const void*, const float*, void*, int, int, int, int, int, int, int,
+                         cudaStream_t);
+static int g_attn_impl = 0;  // 0 = auto (tensor cores for 16-bit storage), 1 = force the fp32 SIMT kernels
+}  // namespace psalm
+
 using namespace psalm;
+
+extern "C" int psalm_set_attention_impl(int impl) {
+  PSALM_REQUIRE(impl == 0 || impl == 1, "set_attention_impl: 0 (auto) or 1 (simt)");
+  g_attn_impl = impl;
+  return PSALM_OK;
+}
 
 #define DISPATCH_T(dt, ...)                                           \
   switch (dt) {                                                       \
@@ -338,6 +354,8 @@ extern "C" int psalm_window_attention(const void* qkv, const void* qkv_bias, con
   const int hd = C / nh;
   const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
   const int nWx = Wp / ws, nW = nWx * (Hp / ws);
+  if (dtype != PSALM_F32 && g_attn_impl == 0 && ws == 12 && hd == 32)
+    return mma_window_attention(qkv, qkv_bias, rel_bias, out, B, H, W, C, nh, shift, dtype, (cudaStream_t)stream);
   AttnDims dm{B * nW, nh, ws * ws, ws * ws, 1, 1.0f / sqrtf((float)hd)};
   int rc = PSALM_OK;
   DISPATCH_T(dtype, {
@@ -350,6 +368,8 @@ extern "C" int psalm_window_attention(const void* qkv, const void* qkv_bias, con
 extern "C" int psalm_causal_attention(const void* qkv, const uint8_t* key_valid, void* out, int B, int T_,
                                       int nh, int hd, int dtype, void* stream) {
   PSALM_REQUIRE(qkv && out, "causal_attention: null pointer");
+  if (dtype != PSALM_F32 && g_attn_impl == 0 && (hd == 32 || hd == 64))
+    return mma_causal_attention(qkv, key_valid, out, B, T_, nh, hd, dtype, (cudaStream_t)stream);
   AttnDims dm{B, nh, T_, T_, 1, 1.0f / sqrtf((float)hd)};
   int rc = PSALM_OK;
   DISPATCH_T(dtype, {
@@ -380,6 +400,9 @@ extern "C" int psalm_cross_attention(const void* q, const void* k, const void* v
                                      int Lk, int nh, int hd, int splits, int dtype, void* stream) {
   PSALM_REQUIRE(q && k && v && out, "cross_attention: null pointer");
   PSALM_REQUIRE(splits >= 1, "cross_attention: splits must be >= 1");
+  if (dtype != PSALM_F32 && g_attn_impl == 0 && (hd == 32 || hd == 64))
+    return mma_cross_attention(q, k, v, mask_bits, row_open, out, workspace, B, Lq, Lk, nh, hd, splits, dtype,
+                               (cudaStream_t)stream);
   AttnDims dm{B, nh, Lq, Lk, splits, 1.0f / sqrtf((float)hd)};
   int rc = PSALM_OK;
   DISPATCH_T(dtype, {

@@ -28,19 +28,34 @@ def sem_seg_postprocess(result, img_size, out_h, out_w):
     return F.interpolate(result, size=(out_h, out_w), mode="bilinear", align_corners=False)[0]
 
 
-def semantic_inference(cls, mask_pred):
-    """softmax(cls)[:, :-1]^T . sigmoid(mask)  (llava_phi.py:402-406) as one library GEMM."""
+def semantic_inference(cls, mask_pred, sig=None, tf32=False):
+    """softmax(cls)[:, :-1]^T . sigmoid(mask)  (llava_phi.py:402-406) as one library GEMM
+    (TF32 tensor cores when the model runs in 16-bit storage, exact fp32 for parity runs)."""
     probs = F.softmax(cls.float(), dim=-1)[:, :-1]
     Q, H, W = mask_pred.shape
-    return torch.matmul(probs.t(), mask_pred.float().sigmoid().view(Q, H * W)).view(-1, H, W)
+    if sig is None:
+        sig = mask_pred.float().sigmoid()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    try:
+        out = torch.matmul(probs.t(), sig.view(Q, H * W)).view(-1, H, W)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return out
 
 
-def _mask_scores(mp):
-    pm = (mp > 0).float()
-    return pm, (mp.sigmoid().flatten(1) * pm.flatten(1)).sum(1) / (pm.flatten(1).sum(1) + 1e-6)
+def query_mask_scores(mask_pred, sig=None):
+    """Per-QUERY mask score  sum(sigmoid * [logit > 0]) / (sum([logit > 0]) + 1e-6)  (llava_phi.py:441-443).
+    It depends only on the query, so it is computed once for the 100 queries instead of once per
+    selected (query, class) pair."""
+    if sig is None:
+        sig = mask_pred.float().sigmoid()
+    pos = mask_pred > 0
+    num = torch.where(pos, sig, torch.zeros((), dtype=sig.dtype, device=sig.device)).flatten(1).sum(1)
+    return num / (pos.flatten(1).sum(1).float() + 1e-6)
 
 
-def instance_inference(cls, mask_pred, topk, is_thing_list=None, panoptic_on=False):
+def instance_inference(cls, mask_pred, topk, is_thing_list=None, panoptic_on=False, sig=None):
     """llava_phi.py:407-447 (topk(sorted=False): order is implementation defined; compare as sets)."""
     scores = F.softmax(cls.float(), dim=-1)[:, :-1]
     nq, nc = scores.shape
@@ -51,48 +66,47 @@ def instance_inference(cls, mask_pred, topk, is_thing_list=None, panoptic_on=Fal
         thing = torch.as_tensor([bool(t) for t in is_thing_list], device=cls.device)
         keep = thing[lab]
         s, lab, qi = s[keep], lab[keep], qi[keep]
-    mp = mask_pred[qi].float()
-    pm, ms = _mask_scores(mp)
+    ms = query_mask_scores(mask_pred, sig)[qi]
     r = Instances(tuple(mask_pred.shape[-2:]))
-    r.pred_masks = pm
-    r.pred_boxes = Boxes(torch.zeros(mp.size(0), 4))
+    r.pred_masks = (mask_pred.index_select(0, qi) > 0).float()
+    r.pred_boxes = Boxes(torch.zeros(qi.shape[0], 4))
     r.scores = s * ms
     r.pred_classes = lab
     r.query_index = qi
     return r
 
 
-def seg_instance_inference(SEG_cls, mask_pred, topk):
+def seg_instance_inference(SEG_cls, mask_pred, topk, sig=None):
     """llava_phi.py:308-324 (referring segmentation)."""
     scores = torch.sigmoid(SEG_cls.float())
     s, idx = scores.flatten(0, 1).topk(topk, sorted=False)
-    mp = mask_pred[idx].float()
-    pm, ms = _mask_scores(mp)
+    ms = query_mask_scores(mask_pred, sig)[idx]
     r = Instances(tuple(mask_pred.shape[-2:]))
-    r.pred_masks = pm
-    r.pred_boxes = Boxes(torch.zeros(mp.size(0), 4))
+    r.pred_masks = (mask_pred.index_select(0, idx) > 0).float()
+    r.pred_boxes = Boxes(torch.zeros(idx.shape[0], 4))
     r.scores = s * ms
     r.query_index = idx
     return r
 
 
-def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8):
+def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8, sig=None):
     """llava_phi.py:325-386 -> (panoptic_seg int32 [H,W], segments_info list)."""
     scores, labels = F.softmax(cls.float(), dim=-1).max(-1)
     nc = cls.shape[-1] - 1
     Q, H, W = mask_pred.shape
-    sig = mask_pred.float().sigmoid()
+    if sig is None:
+        sig = mask_pred.float().sigmoid()
     keep = labels.ne(nc) & (scores > obj_thr)
-    # argmax over kept queries only: non-kept rows get -1 (< any kept score*sigmoid >= 0)
-    prob = torch.where(keep.view(-1, 1, 1), scores.view(-1, 1, 1) * sig, torch.full_like(sig, -1.0))
-    ids = prob.argmax(0)                                   # [H,W] query index
-    ge = sig >= 0.5
-    onehot = F.one_hot(ids.view(-1), Q).t().view(Q, H, W).bool()
-    area = onehot.flatten(1).sum(1)
-    orig = ge.flatten(1).sum(1)
-    inter = (onehot & ge).flatten(1).sum(1)
+    # argmax over kept queries only: non-kept rows evaluate to -1 (< any kept score * sigmoid >= 0)
+    wq = torch.where(keep, scores, torch.zeros_like(scores)).view(Q, 1, 1)
+    neg = (keep.float() - 1.0).view(Q, 1, 1)
+    ids = torch.addcmul(neg, sig, wq).argmax(0).view(-1)                  # [H*W] query index
+    in_mask = mask_pred.view(Q, -1).gather(0, ids.view(1, -1)).view(-1) >= 0   # sigmoid >= 0.5 at the winner
+    area = torch.bincount(ids, minlength=Q)
+    inter = torch.bincount(ids, weights=in_mask.float(), minlength=Q).long()
+    orig = (mask_pred >= 0).flatten(1).sum(1)
     host = torch.stack([keep.long(), labels.long(), area, orig, inter], 0).cpu().numpy()   # the one D2H copy
-    seg_of_query = np.zeros(Q + 1, np.int32)
+    seg_of_query = np.zeros(Q, np.int32)
     info, stuff, cur = [], {}, 0
     if host[0].sum() == 0:
         return torch.zeros((H, W), dtype=torch.int32, device=cls.device), info
@@ -113,6 +127,5 @@ def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8):
             seg_of_query[q] = cur
             info.append(dict(id=cur, isthing=isthing, category_id=pc))
     lut = torch.from_numpy(seg_of_query).to(cls.device)
-    in_mask = torch.gather(ge.view(Q, -1), 0, ids.view(1, -1)).view(H, W)   # sig[ids[p], p] >= 0.5
     pan = torch.where(in_mask, lut[ids], torch.zeros((), dtype=torch.int32, device=cls.device))
-    return pan.to(torch.int32), info
+    return pan.view(H, W).to(torch.int32), info

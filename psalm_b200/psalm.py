@@ -47,8 +47,9 @@ class PSALMModel:
 
 class PSALM:
     def __init__(self, state_dict, cfg: PsalmConfig = PsalmConfig(), dtype=torch.bfloat16, device="cuda",
-                 seg_task="panoptic"):
+                 seg_task="panoptic", use_cuda_graph=False):
         self._check_runtime(device)
+        self.use_cuda_graph = use_cuda_graph
         if dtype == torch.float32:  # true fp32 for parity runs (cuDNN would otherwise pick TF32)
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
@@ -128,6 +129,46 @@ class PSALM:
         out["mask_size"] = sizes[0]
         return out
 
+    # ---- CUDA-graph replay of the device-only part -------------------------------------------------
+    def forward_core_graphed(self, images, plan):
+        """Same results as forward_core, replayed from a CUDA graph captured per (image size, prompt
+        structure): the ~2000 launches of one image become one graph launch (the reference issues them
+        one by one from Python, plus ~150 extra tiny launches in its decoder)."""
+        key = (tuple(images.shape), plan.B, plan.T, plan.n_img, plan.any_padding,
+               None if plan.cls_pool is None else tuple(plan.cls_pool.shape), plan.refer_pool is not None,
+               None if plan.pad_pos is None else int(plan.pad_pos.numel()))
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        tensors = ("tok_ids", "img_pos", "seg_pos", "pad_pos", "attention_mask", "cls_pool", "refer_pool")
+        if ent is None:
+            import copy
+            static_img = images.clone()
+            static_plan = copy.copy(plan)
+            for n in tensors:
+                t = getattr(plan, n)
+                setattr(static_plan, n, None if t is None else t.clone())
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.forward_core(static_img, static_plan)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self.forward_core(static_img, static_plan)
+            ent = (g, static_img, static_plan, static_out)
+            self._graphs[key] = ent
+        g, static_img, static_plan, static_out = ent
+        static_img.copy_(images, non_blocking=True)
+        for n in tensors:
+            t = getattr(plan, n)
+            if t is not None:
+                getattr(static_plan, n).copy_(t, non_blocking=True)
+        g.replay()
+        return static_out
+
     def make_plan(self, input_ids, attention_mask, image_hw, class_name_ids=None, cls_indices=None,
                   class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None):
         H, W = image_hw
@@ -150,7 +191,7 @@ class PSALM:
         images_d = images.to(self.device, non_blocking=True)
         plan = self.make_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
                               class_name_embedding_indices, token_refer_id, refer_embedding_indices).to(self.device)
-        out = self.forward_core(images_d, plan)
+        out = self.forward_core_graphed(images_d, plan) if self.use_cuda_graph else self.forward_core(images_d, plan)
         return self.post_process(out, images.shape[-2:], seg_info)
 
     @torch.no_grad()
@@ -173,20 +214,23 @@ class PSALM:
             if self.sem_seg_postprocess_before_inference:
                 mp = PP.sem_seg_postprocess(mp, (oh, ow), height, width)
             cls = out["pred_class_name_logits"][b].float() if out["pred_class_name_logits"] is not None else None
+            mp = mp.contiguous()
+            sig = mp.sigmoid()   # shared by the task heads below (the reference recomputes it per head)
+            tf32 = self.dtype != torch.float32
             if self.semantic_on:
-                sem = PP.semantic_inference(cls, mp)
+                sem = PP.semantic_inference(cls, mp, sig, tf32)
                 if not self.sem_seg_postprocess_before_inference:
                     sem = PP.sem_seg_postprocess(sem, (oh, ow), height, width)
                 r["sem_seg"] = sem
             if self.instance_on:
                 r["instances"] = PP.instance_inference(cls, mp, self.test_topk_per_image,
-                                                       getattr(self, "is_thing_list", None), self.panoptic_on)
+                                                       getattr(self, "is_thing_list", None), self.panoptic_on, sig)
             if self.panoptic_on:
                 r["panoptic_seg"] = PP.panoptic_inference(cls, mp, self.is_thing_list,
                                                           self.cfg.mask.object_mask_threshold,
-                                                          self.cfg.mask.overlap_threshold)
+                                                          self.cfg.mask.overlap_threshold, sig)
             if self.referring_on:
                 r["instances"] = PP.seg_instance_inference(out["pred_SEG_logits"][b].float(), mp,
-                                                           self.test_topk_per_image)
+                                                           self.test_topk_per_image, sig)
             results.append(r)
         return results

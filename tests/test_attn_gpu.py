@@ -11,6 +11,15 @@ DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 TOL = {"f32": 2e-5, "f16": 2e-3, "bf16": 1.2e-2}   # max |err| / max |ref|; 16-bit = output rounding
 
 
+@pytest.fixture(params=["auto", "simt"], autouse=True)
+def attn_impl(request):
+    """auto = tensor-core (mma.sync) kernels for fp16/bf16 + SIMT for fp32; simt = fp32-math kernels for all."""
+    from psalm_b200 import _lib
+    _lib.check(_lib.lib().psalm_set_attention_impl(1 if request.param == "simt" else 0), "set_attention_impl")
+    yield request.param
+    _lib.lib().psalm_set_attention_impl(0)
+
+
 def _close(out, ref, dt, scale=1.0):
     out, ref = out.float().cpu(), ref.float().cpu()
     err = (out - ref).abs().max() / (ref.abs().max() + 1e-30)
