@@ -236,13 +236,11 @@ def run_ours(args, rank, world, local_rank):
     d2h = sum(sum(t.numel() * t.element_size() for t in h) for h in host)
 
     # ---------------- reductions over ranks: max time, gather of compact predictions ----------------
-    t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rec = torch.zeros(B, 100, 2, device=dev)       # (score, class) per query: the metric reduction payload
-        gathered = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(gathered, rec)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    from psalm_b200 import dist as PD
+    res_last = step_device()
+    records = PD.gather_records(torch.stack([PD.compact_record(r) for r in res_last]))   # the one NCCL all_gather
+    assert records.shape[0] == B * world
+    ms_total, e2e_ms = PD.max_over_ranks([ms_total, e2e_s * 1e3], dev)
     if rank != 0:
         return
     images_total = K * B * world

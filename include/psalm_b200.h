@@ -135,6 +135,20 @@ int psalm_bilinear_tokens(const void* in, void* out, int B, int Hi, int Wi, int 
 int psalm_attn_mask_bits(const void* logits, uint32_t* bits, uint8_t* row_open, int rows, int P, int dtype,
                          void* stream);
 
+/* Fused residual add + LayerNorm:  s = x (+ r1) (+ r2);  y = LN(s) * weight + bias;  sum_out (nullable)
+ * receives s.  Replaces the `x = shortcut + ...; norm(x)` pairs of swin_trans.py:207,247-251, the
+ * parallel-residual sum of PhiDecoderLayer followed by the next input_layernorm, and the post-norm
+ * layers of msdeformattn.py:59-65 / mask2former_transformer_decoder.py:42-43,102-103,160-161.
+ * x, r1, r2, y, sum_out: [rows, C]; C in {128,256,512,1024,2048}; fp32 statistics (two-pass). */
+int psalm_add_layernorm(const void* x, const void* r1, const void* r2, const void* weight, const void* bias,
+                        void* sum_out, void* y, long long rows, int C, float eps, int dtype, void* stream);
+
+/* GroupNorm (+ optional ReLU) of a token-major map x [B,N,C] (statistics over N x C/groups per group),
+ * msdeformattn.py:199-203,244-252.  stats_workspace: 2*B*groups doubles. */
+int psalm_groupnorm_tokens(const void* x, const void* weight, const void* bias, void* y,
+                           double* stats_workspace, int B, int N, int C, int groups, float eps, int relu,
+                           int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

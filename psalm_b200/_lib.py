@@ -41,6 +41,8 @@ SIGNATURES = {
     "psalm_mask_logits": ([_c_vp] * 3 + [_c_i] * 6 + [_c_vp], _c_i),
     "psalm_bilinear_tokens": ([_c_vp] * 2 + [_c_i] * 9 + [_c_vp], _c_i),
     "psalm_attn_mask_bits": ([_c_vp] * 3 + [_c_i] * 3 + [_c_vp], _c_i),
+    "psalm_add_layernorm": ([_c_vp] * 7 + [ctypes.c_longlong, _c_i, ctypes.c_float, _c_i, _c_vp], _c_i),
+    "psalm_groupnorm_tokens": ([_c_vp] * 5 + [_c_i] * 4 + [ctypes.c_float, _c_i, _c_i, _c_vp], _c_i),
 }
 
 

@@ -46,6 +46,15 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
   }
 }
 
+// 16-byte async global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(a), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -58,8 +67,11 @@ struct CausalMma {
   T* out;                    // [B,T,nh*hd]
   int T_, nh, hd;
   static constexpr bool kCausal = true;
+  __device__ __forceinline__ const T* ptr(int which, int b, int h, int n, int d0) const {
+    return qkv + (((size_t)b * T_ + n) * 3 + which) * nh * hd + h * hd + d0;
+  }
   __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
-    return ldg16(qkv + (((size_t)b * T_ + n) * 3 + which) * nh * hd + h * hd + d0);
+    return ldg16(ptr(which, b, h, n, d0));
   }
   __device__ __forceinline__ float score(int b, int h, int qi, int kj, float s) const {
     if (kj > qi) return -INFINITY;
@@ -82,10 +94,13 @@ struct CrossMma {
   T* out;
   int Lq, Lk, nh, hd, W32;
   static constexpr bool kCausal = false;
-  __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
+  __device__ __forceinline__ const T* ptr(int which, int b, int h, int n, int d0) const {
     const T* base = which == 0 ? q : (which == 1 ? k : v);
     const int L = which == 0 ? Lq : Lk;
-    return ldg16(base + ((size_t)b * L + n) * nh * hd + h * hd + d0);
+    return base + ((size_t)b * L + n) * nh * hd + h * hd + d0;
+  }
+  __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
+    return ldg16(ptr(which, b, h, n, d0));
   }
   __device__ __forceinline__ float score(int b, int h, int qi, int kj, float s) const {
     if (bits) {
@@ -109,11 +124,12 @@ template <typename T, int HD, typename Policy>
 __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm, float* __restrict__ part) {
   constexpr int BQ = 64, BK = 64, LD = HD + 8;
   __shared__ __align__(16) T Qs[BQ * LD];
-  __shared__ __align__(16) T Ks[BK * LD];
-  __shared__ __align__(16) T Vs[BK * LD];
+  __shared__ __align__(16) T KVs[2][2][BK * LD];   // [stage][K|V]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int qt = blockIdx.x / dm.splits, sp = blockIdx.x - qt * dm.splits;
+  // heavy (late, causal) query tiles first: better tail balance
+  const int nqt = (dm.Lq + BQ - 1) / BQ;
+  const int qt = nqt - 1 - (int)(blockIdx.x / dm.splits), sp = blockIdx.x % dm.splits;
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * BQ;
   const int ktiles = (dm.Lk + BK - 1) / BK;
@@ -144,20 +160,29 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
   const float sc = dm.scale;
 
-  for (int kt = kt0; kt < kt1; ++kt) {
-    __syncthreads();
+  auto prefetch = [&](int kt, int stage) {
     for (int i = tid; i < BK * HD / 8; i += 128) {
       const int row = i / (HD / 8), d0 = (i % (HD / 8)) * 8;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
       const int kj = kt * BK + row;
-      if (kj < dm.Lk) {
-        kv = pol.load8(1, b, h, kj, d0);
-        vv = pol.load8(2, b, h, kj, d0);
-      }
-      *reinterpret_cast<uint4*>(&Ks[row * LD + d0]) = kv;
-      *reinterpret_cast<uint4*>(&Vs[row * LD + d0]) = vv;
+      const bool ok = kj < dm.Lk;
+      const int kc = ok ? kj : 0;
+      cp_async16(&KVs[stage][0][row * LD + d0], pol.ptr(1, b, h, kc, d0), ok ? 16 : 0);
+      cp_async16(&KVs[stage][1][row * LD + d0], pol.ptr(2, b, h, kc, d0), ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  if (kt0 < kt1) prefetch(kt0, 0);
+  for (int kt = kt0; kt < kt1; ++kt) {
+    const int stage = (kt - kt0) & 1;
+    if (kt + 1 < kt1) {
+      prefetch(kt + 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const T* Ks = KVs[stage][0];
+    const T* Vs = KVs[stage][1];
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -234,6 +259,7 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
         mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
       }
     }
+    __syncthreads();   // every warp is done with this stage before it is refilled
   }
   // ---- epilogue
   if (dm.splits == 1) {

@@ -238,6 +238,14 @@ __global__ void msda_scalar_kernel(const TV* __restrict__ value, const TL* __res
 // -------------------------------------------------------------------------------------------
 // Fused encoder kernel: raw offsets + logits -> softmax, reference points, sampling.
 //   ow [B, Lq, M*L*P*2 + M*L*P]; value head-major [B, M, S, D]; Lq == S; patch mapping.
+//
+// The kernel is instruction-issue bound, not memory bound (ncu, profiles/r1_msda_fused_ncu.txt:
+// issue slots 69 % busy, DRAM 6 %), so the per-sample scalar work is NOT replicated across the G
+// lanes that share a (query, head): each lane derives the parameters of LP/G samples (softmax
+// weight, clamped corner index, the four bilinear x attention weights with the zero-padding
+// predicates folded in as zero weights) and the group exchanges them with warp shuffles — 5 SHFL per
+// sample instead of ~90 ALU instructions per lane.  Corner loads are unconditional (clamped
+// addresses), 16 bytes per lane.
 // -------------------------------------------------------------------------------------------
 template <typename TV, typename TO, int G, int LT, int PT>
 __global__ void __launch_bounds__(kThreads)
@@ -246,64 +254,84 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
   constexpr int CH = 16 / sizeof(TV);
   constexpr int NG = kThreads / G;
   constexpr int LP = LT * PT;
+  constexpr int SPL = (LP + G - 1) / G;   // samples owned per lane
   const int g = threadIdx.x / G, cl = threadIdx.x % G;
+  const int lane = threadIdx.x & 31;
+  const int gbase = lane - cl;            // first lane of this group inside the warp
   const int m = blockIdx.y, b = blockIdx.z;
   int q, ql, qy, qx;
-  if (!resolve_query<NG>(lv, true, g, S, q, ql, qy, qx)) return;
-
+  const bool active = resolve_query<NG>(lv, true, g, S, q, ql, qy, qx);
+  if (!active) {  // ragged tile edge: keep the lanes alive for the shuffles, on a valid dummy query
+    q = lv.start[ql];
+    qy = qx = 0;
+  }
   const size_t row = ((size_t)b * S + q) * (size_t)(M * LP * 3);
   const TO* __restrict__ offp = ow + row + (size_t)m * LP * 2;
   const TO* __restrict__ lgp = ow + row + (size_t)M * LP * 2 + (size_t)m * LP;
 
-  // raw offsets (2*LP values) and logits (LP values) of this (query, head), vector loads
-  float offv[2 * LP], lg[LP];
-  if constexpr (sizeof(TO) == 4) {
-    const float4* o4 = reinterpret_cast<const float4*>(offp);
-#pragma unroll
-    for (int i = 0; i < LP / 2; ++i) {
-      const float4 v = __ldg(o4 + i);
-      offv[4 * i] = v.x; offv[4 * i + 1] = v.y; offv[4 * i + 2] = v.z; offv[4 * i + 3] = v.w;
-    }
-    const float4* g4 = reinterpret_cast<const float4*>(lgp);
-#pragma unroll
-    for (int i = 0; i < LP / 4; ++i) {
-      const float4 v = __ldg(g4 + i);
-      lg[4 * i] = v.x; lg[4 * i + 1] = v.y; lg[4 * i + 2] = v.z; lg[4 * i + 3] = v.w;
-    }
-  } else {
-    // 16-bit rows: offsets are 2*LP*2 B (16-byte multiples for LP % 4 == 0), logits LP*2 B (8-byte)
-    const uint4* o4 = reinterpret_cast<const uint4*>(offp);
-#pragma unroll
-    for (int i = 0; i < LP / 4; ++i) {
-      const uint4 v = __ldg(o4 + i);
-      unpack2<TO>(v.x, offv[8 * i], offv[8 * i + 1]);
-      unpack2<TO>(v.y, offv[8 * i + 2], offv[8 * i + 3]);
-      unpack2<TO>(v.z, offv[8 * i + 4], offv[8 * i + 5]);
-      unpack2<TO>(v.w, offv[8 * i + 6], offv[8 * i + 7]);
-    }
-    const uint2* g2 = reinterpret_cast<const uint2*>(lgp);
-#pragma unroll
-    for (int i = 0; i < LP / 4; ++i) {
-      const uint2 v = __ldg(g2 + i);
-      unpack2<TO>(v.x, lg[4 * i], lg[4 * i + 1]);
-      unpack2<TO>(v.y, lg[4 * i + 2], lg[4 * i + 3]);
-    }
-  }
-  // softmax over the L*P logits of this (query, head)  (F.softmax, ms_deform_attn.py:105)
+  // ---- softmax over the L*P logits (F.softmax, ms_deform_attn.py:105), split across the group
+  float lg[SPL];
   float mx = -INFINITY;
 #pragma unroll
-  for (int s = 0; s < LP; ++s) mx = fmaxf(mx, lg[s]);
+  for (int j = 0; j < SPL; ++j) {
+    const int s = cl + j * G;
+    lg[j] = s < LP ? to_f32<TO>(lgp[s]) : -INFINITY;
+    mx = fmaxf(mx, lg[j]);
+  }
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
 #pragma unroll
-  for (int s = 0; s < LP; ++s) {
-    lg[s] = expf(lg[s] - mx);
-    sum += lg[s];
+  for (int j = 0; j < SPL; ++j) {
+    lg[j] = (cl + j * G) < LP ? expf(lg[j] - mx) : 0.f;
+    sum += lg[j];
   }
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.f / sum;
 
   // reference point = pixel centre of the query, normalised (msdeformattn.py:76-87)
   const float rx = ((float)qx + 0.5f) / (float)lv.W[ql];
   const float ry = ((float)qy + 0.5f) / (float)lv.H[ql];
+
+  // ---- parameters of the samples this lane owns
+  uint32_t pidx[SPL];
+  float pw[SPL][4];
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int s = cl + j * G;
+    pidx[j] = 0;
+    pw[j][0] = pw[j][1] = pw[j][2] = pw[j][3] = 0.f;
+    if (s < LP) {
+      const int l = s / PT;
+      const int H = lv.H[l], W = lv.W[l];
+      float ox, oy;
+      if constexpr (sizeof(TO) == 4) {
+        const float2 o2 = __ldg(reinterpret_cast<const float2*>(offp) + s);
+        ox = o2.x; oy = o2.y;
+      } else {
+        unpack2<TO>(__ldg(reinterpret_cast<const uint32_t*>(offp) + s), ox, oy);
+      }
+      // sampling_locations = ref + off / (W_l, H_l)  (ms_deform_attn.py:109-110), then the
+      // kernel-side  w_im = loc_w * W - 0.5  (ms_deform_im2col_cuda.cuh:290-291)
+      const float x = (rx + ox / (float)W) * (float)W - 0.5f;
+      const float y = (ry + oy / (float)H) * (float)H - 0.5f;
+      if (y > -1.f && x > -1.f && y < (float)H && x < (float)W) {
+        const float yf = floorf(y), xf = floorf(x);
+        const int y0 = (int)yf, x0 = (int)xf;
+        const float ly = y - yf, lx = x - xf, hy = 1.f - ly, hx = 1.f - lx;
+        const float aw = lg[j] * inv;
+        const bool vy0 = y0 >= 0, vy1 = y0 + 1 <= H - 1, vx0 = x0 >= 0, vx1 = x0 + 1 <= W - 1;
+        pw[j][0] = (vy0 && vx0) ? hy * hx * aw : 0.f;
+        pw[j][1] = (vy0 && vx1) ? hy * lx * aw : 0.f;
+        pw[j][2] = (vy1 && vx0) ? ly * hx * aw : 0.f;
+        pw[j][3] = (vy1 && vx1) ? ly * lx * aw : 0.f;
+        const int y0c = y0 < 0 ? 0 : y0, x0c = x0 < 0 ? 0 : x0;
+        const int y1c = y0 + 1 > H - 1 ? H - 1 : y0 + 1, x1c = x0 + 1 > W - 1 ? W - 1 : x0 + 1;
+        pidx[j] = (uint32_t)(y0c * W + x0c) | ((uint32_t)(x1c - x0c) << 30) | ((uint32_t)(y1c - y0c) << 31);
+      }
+    }
+  }
 
   const TV* __restrict__ vb = value + ((size_t)b * M + m) * (size_t)S * D + cl * CH;
   float acc[CH];
@@ -311,21 +339,31 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
   for (int i = 0; i < CH; ++i) acc[i] = 0.f;
 
 #pragma unroll
-  for (int l = 0; l < LT; ++l) {
-    const int H = lv.H[l], W = lv.W[l];
-    const TV* __restrict__ vl = vb + (size_t)lv.start[l] * D;
+  for (int s = 0; s < LP; ++s) {
+    const int l = s / PT, owner = gbase + (s % G), j = s / G;
+    const uint32_t pk = __shfl_sync(0xffffffffu, pidx[j], owner);
+    const float w00 = __shfl_sync(0xffffffffu, pw[j][0], owner);
+    const float w01 = __shfl_sync(0xffffffffu, pw[j][1], owner);
+    const float w10 = __shfl_sync(0xffffffffu, pw[j][2], owner);
+    const float w11 = __shfl_sync(0xffffffffu, pw[j][3], owner);
+    const int W = lv.W[l];
+    const TV* p00 = vb + ((size_t)lv.start[l] + (pk & 0x3fffffffu)) * D;
+    const TV* p01 = p00 + ((pk >> 30) & 1u) * D;
+    const size_t dyo = (size_t)(pk >> 31) * W * D;
+    float f00[CH], f01[CH], f10[CH], f11[CH];
+    load16_as_f32<TV>(p00, f00);
+    load16_as_f32<TV>(p01, f01);
+    load16_as_f32<TV>(p00 + dyo, f10);
+    load16_as_f32<TV>(p01 + dyo, f11);
 #pragma unroll
-    for (int p = 0; p < PT; ++p) {
-      const int s = l * PT + p;
-      const float ox = offv[2 * s], oy = offv[2 * s + 1];
-      // sampling_locations = ref + off / (W_l, H_l)  (ms_deform_attn.py:109-110), then the
-      // kernel-side  w_im = loc_w * W - 0.5  (ms_deform_im2col_cuda.cuh:290-291)
-      const float x = (rx + ox / (float)W) * (float)W - 0.5f;
-      const float y = (ry + oy / (float)H) * (float)H - 0.5f;
-      sample_accumulate<TV>(vl, H, W, D, x, y, lg[s] * inv, acc);
+    for (int i = 0; i < CH; ++i) {
+      acc[i] = fmaf(w00, f00[i], acc[i]);
+      acc[i] = fmaf(w01, f01[i], acc[i]);
+      acc[i] = fmaf(w10, f10[i], acc[i]);
+      acc[i] = fmaf(w11, f11[i], acc[i]);
     }
   }
-  store16_from_f32<TV>(out + (((size_t)b * S + q) * M + m) * (size_t)D + cl * CH, acc);
+  if (active) store16_from_f32<TV>(out + (((size_t)b * S + q) * M + m) * (size_t)D + cl * CH, acc);
 }
 
 // -------------------------------------------------------------------------------------------

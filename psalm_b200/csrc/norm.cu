@@ -1,0 +1,236 @@
+// Normalisation kernels of the hot path (HBM-bound streaming work, fp32 statistics):
+//   add_layernorm   s = x (+ r1) (+ r2);  y = LayerNorm(s) * w + b;  optionally also writes s.
+//                   Replaces the residual `add` + nn.LayerNorm pairs of SwinTransformerBlock
+//                   (swin_trans.py:207,247-251), PhiDecoderLayer (attn + mlp + residual, then the next
+//                   input_layernorm), the encoder / decoder post-norm layers (msdeformattn.py:59-65,
+//                   mask2former_transformer_decoder.py:42-43,102-103,160-161).  One warp per row,
+//                   the row lives in registers (two-pass mean / variance like ATen), 16-byte accesses.
+//   groupnorm_tokens  GroupNorm(32) on a TOKEN-MAJOR map [B, N, C] (+ optional ReLU): partial
+//                   sum / sum-of-squares per (batch, group) with one atomicAdd(double) per CTA, then a
+//                   streaming apply pass (msdeformattn.py:199-203,244-252 conv+GN(+ReLU) blocks).
+#include "common.cuh"
+
+namespace psalm {
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&f)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    unpack2<T>(v.x, f[0], f[1]);
+    unpack2<T>(v.y, f[2], f[3]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&f)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  } else {
+    uint2 v;
+    v.x = pack2<T>(f[0], f[1]);
+    v.y = pack2<T>(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+}
+
+// CPL = 4-element chunks per lane; C = 128 * CPL
+template <typename T, int CPL>
+__global__ void __launch_bounds__(128) add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ r1,
+                                                            const T* __restrict__ r2, const T* __restrict__ w,
+                                                            const T* __restrict__ b, T* __restrict__ sum_out,
+                                                            T* __restrict__ y, long long rows, float eps) {
+  constexpr int C = 128 * CPL;
+  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const size_t base = (size_t)row * C;
+  float v[CPL][4];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int off = (c * 32 + lane) * 4;
+    load4<T>(x + base + off, v[c]);
+    if (r1) {
+      float t[4];
+      load4<T>(r1 + base + off, t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[c][i] += t[i];
+    }
+    if (r2) {
+      float t[4];
+      load4<T>(r2 + base + off, t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[c][i] += t[i];
+    }
+    if (sum_out) {
+      // the residual stream is stored in T: normalise what the next consumer will actually read
+      store4<T>(sum_out + base + off, v[c]);
+      if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[c][i] = to_f32<T>(from_f32<T>(v[c][i]));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += v[c][i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d = v[c][i] - mean;
+      q = fmaf(d, d, q);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.f / C) + eps);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int off = (c * 32 + lane) * 4;
+    float g[4], bb[4], o4[4];
+    load4<T>(w + off, g);
+    load4<T>(b + off, bb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o4[i] = (v[c][i] - mean) * rstd * g[i] + bb[i];
+    store4<T>(y + base + off, o4);
+  }
+}
+
+// ---- GroupNorm on token-major maps -----------------------------------------------------------------
+// stats[b, g] = (sum, sumsq) as double; grid = (chunks, B), block 256; C <= 1024, C % (4*groups) == 0
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
+                                                              int N, int C, int groups, int tokens_per_cta) {
+  __shared__ float ssum[64], ssq[64];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tokens_per_cta;
+  const int t1 = min(N, t0 + tokens_per_cta);
+  const int cpg = C / groups;
+  if (threadIdx.x < 64) ssum[threadIdx.x] = ssq[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int chunks = C / 4;                         // 4-element chunks per token
+  const int tpb = 256 / chunks > 0 ? 256 / chunks : 1;   // tokens processed concurrently
+  const int cidx = threadIdx.x % chunks, trow = threadIdx.x / chunks;
+  float s = 0.f, q = 0.f;
+  if (trow < tpb) {
+    for (int t = t0 + trow; t < t1; t += tpb) {
+      float f[4];
+      load4<T>(x + ((size_t)b * N + t) * C + cidx * 4, f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s += f[i];
+        q = fmaf(f[i], f[i], q);
+      }
+    }
+    const int g = (cidx * 4) / cpg;
+    atomicAdd(&ssum[g], s);
+    atomicAdd(&ssq[g], q);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    atomicAdd(&stats[((size_t)b * groups + threadIdx.x) * 2], (double)ssum[threadIdx.x]);
+    atomicAdd(&stats[((size_t)b * groups + threadIdx.x) * 2 + 1], (double)ssq[threadIdx.x]);
+  }
+}
+
+template <typename T>
+__global__ void groupnorm_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats,
+                                       const T* __restrict__ w, const T* __restrict__ bias, T* __restrict__ y,
+                                       int B, int N, int C, int groups, float eps, int relu) {
+  const int cpg = C / groups;
+  const long long n4 = (long long)B * N * C / 4;
+  const double cnt = (double)N * cpg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const int c = (int)(e % C);
+    const int b = (int)(e / ((long long)N * C));
+    const int g = c / cpg;
+    const double m = stats[((size_t)b * groups + g) * 2] / cnt;
+    const double var = stats[((size_t)b * groups + g) * 2 + 1] / cnt - m * m;
+    const float mean = (float)m, rstd = rsqrtf((float)(var > 0 ? var : 0) + eps);
+    float f[4], gw[4], gb[4], o[4];
+    load4<T>(x + e, f);
+    load4<T>(w + c, gw);
+    load4<T>(bias + c, gb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[k] = (f[k] - mean) * rstd * gw[k] + gb[k];
+      if (relu) o[k] = fmaxf(o[k], 0.f);
+    }
+    store4<T>(y + e, o);
+  }
+}
+
+template <typename T>
+static int launch_ln(const void* x, const void* r1, const void* r2, const void* w, const void* b, void* sum_out,
+                     void* y, long long rows, int C, float eps, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+#define LN(CPL)                                                                                               \
+  add_layernorm_kernel<T, CPL><<<grid, 128, 0, st>>>((const T*)x, (const T*)r1, (const T*)r2, (const T*)w,     \
+                                                     (const T*)b, (T*)sum_out, (T*)y, rows, eps)
+  switch (C) {
+    case 128: LN(1); break;
+    case 256: LN(2); break;
+    case 512: LN(4); break;
+    case 1024: LN(8); break;
+    case 2048: LN(16); break;
+    default: set_error("add_layernorm: C=%d unsupported (128/256/512/1024/2048)", C); return PSALM_E_UNSUPPORTED;
+  }
+#undef LN
+  return check_launch("add_layernorm_kernel");
+}
+
+template <typename T>
+static int launch_gn(const void* x, const void* w, const void* b, void* y, double* stats, int B, int N, int C,
+                     int groups, float eps, int relu, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, st);
+  if (e != cudaSuccess) { set_error("groupnorm: memset failed: %s", cudaGetErrorString(e)); return PSALM_E_CUDA; }
+  const int tokens_per_cta = 256;
+  dim3 g1((N + tokens_per_cta - 1) / tokens_per_cta, B);
+  groupnorm_stats_kernel<T><<<g1, 256, 0, st>>>((const T*)x, stats, N, C, groups, tokens_per_cta);
+  const long long n4 = (long long)B * N * C / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  groupnorm_apply_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>((const T*)x, stats, (const T*)w, (const T*)b, (T*)y,
+                                                                     B, N, C, groups, eps, relu);
+  return check_launch("groupnorm_tokens");
+}
+
+}  // namespace psalm
+
+using namespace psalm;
+
+extern "C" int psalm_add_layernorm(const void* x, const void* r1, const void* r2, const void* weight,
+                                   const void* bias, void* sum_out, void* y, long long rows, int C, float eps,
+                                   int dtype, void* stream) {
+  PSALM_REQUIRE(x && weight && bias && y, "add_layernorm: null pointer");
+  PSALM_REQUIRE(rows > 0 && rows < (1ll << 33), "add_layernorm: bad row count");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case PSALM_F32: return launch_ln<float>(x, r1, r2, weight, bias, sum_out, y, rows, C, eps, st);
+    case PSALM_F16: return launch_ln<__half>(x, r1, r2, weight, bias, sum_out, y, rows, C, eps, st);
+    case PSALM_BF16: return launch_ln<__nv_bfloat16>(x, r1, r2, weight, bias, sum_out, y, rows, C, eps, st);
+  }
+  set_error("add_layernorm: unknown dtype %d", dtype);
+  return PSALM_E_ARG;
+}
+
+extern "C" int psalm_groupnorm_tokens(const void* x, const void* weight, const void* bias, void* y,
+                                      double* stats_workspace, int B, int N, int C, int groups, float eps,
+                                      int relu, int dtype, void* stream) {
+  PSALM_REQUIRE(x && weight && bias && y && stats_workspace, "groupnorm_tokens: null pointer");
+  PSALM_REQUIRE(groups > 0 && groups <= 64 && C % (4 * groups) == 0 && C <= 1024 && 256 % (C / 4) == 0,
+                "groupnorm_tokens: unsupported C=%d groups=%d", C, groups);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case PSALM_F32: return launch_gn<float>(x, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
+    case PSALM_F16: return launch_gn<__half>(x, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
+    case PSALM_BF16: return launch_gn<__nv_bfloat16>(x, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
+  }
+  set_error("groupnorm_tokens: unknown dtype %d", dtype);
+  return PSALM_E_ARG;
+}

@@ -82,9 +82,9 @@ def causal_attention(qkv, key_valid, B, T, nh, hd):
 
 def pick_splits(B, nh, Lq, Lk):
     """Split-K factor so that a 100-query problem still fills ~2 waves of 148 SMs."""
-    ctas = B * nh * ((Lq + 31) // 32)
+    ctas = B * nh * ((Lq + 63) // 64)
     want = max(1, (2 * 148 + ctas - 1) // ctas)
-    return int(max(1, min(want, (Lk + 255) // 256)))
+    return int(max(1, min(want, (Lk + 127) // 128)))
 
 
 def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, workspace=None):
@@ -156,3 +156,44 @@ def attn_mask_bits(logits):
     _lib.check(rc, "psalm_attn_mask_bits")
     _count()
     return bits, row_open
+
+
+_LN_WIDTHS = (128, 256, 512, 1024, 2048)
+
+
+def add_layer_norm(x, weight, bias, eps=1e-5, r1=None, r2=None, return_sum=False):
+    """y = LayerNorm(x + r1 + r2) (residuals optional); with return_sum also returns the summed stream."""
+    C = x.shape[-1]
+    if C not in _LN_WIDTHS:
+        raise _lib.PsalmKernelError("add_layer_norm: width %d unsupported" % C)
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")):
+        _chk(t, "add_layer_norm." + n)
+    for t in (r1, r2):
+        if t is not None:
+            _chk(t, "add_layer_norm.residual")
+            if t.shape != x.shape or t.dtype != x.dtype:
+                raise _lib.PsalmKernelError("add_layer_norm: residual shape / dtype mismatch")
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if return_sum else None
+    rc = _lib.lib().psalm_add_layernorm(
+        _lib.ptr(x), _lib.ptr(r1) if r1 is not None else None, _lib.ptr(r2) if r2 is not None else None,
+        _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(s) if s is not None else None, _lib.ptr(y),
+        x.numel() // C, C, float(eps), _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
+    _lib.check(rc, "psalm_add_layernorm")
+    _count()
+    return (s, y) if return_sum else y
+
+
+def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False):
+    """GroupNorm(groups) (+ReLU) of a token-major map [B,N,C]."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")):
+        _chk(t, "group_norm_tokens." + n)
+    B, N, C = x.shape
+    stats = torch.empty(2 * B * groups, dtype=torch.float64, device=x.device)
+    y = torch.empty_like(x)
+    rc = _lib.lib().psalm_groupnorm_tokens(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(stats),
+                                           B, N, C, groups, float(eps), 1 if relu else 0,
+                                           _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
+    _lib.check(rc, "psalm_groupnorm_tokens")
+    _count(2)
+    return y

@@ -60,7 +60,7 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
         return x
 
     def _heads_common(self, output):
-        dec = F.layer_norm(output, (self.cfg.hidden,), self.w["dn.w"], self.w["dn.b"])
+        dec = kernels.add_layer_norm(output.contiguous(), self.w["dn.w"], self.w["dn.b"])
         return dec, self._mlp("mask_embed", 3, dec)
 
     # reference-surface entry: NCHW maps in, dict out (mask2former_transformer_decoder.py:488,684-692)
@@ -96,7 +96,7 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
         # attention-mask sources: mask_features interpolated once to each target size (see module docstring)
         pooled = [kernels.bilinear_tokens(mask_features, H4, W4, hl, wl) for hl, wl in ms_sizes]
         qpos = self.query_embed.unsqueeze(0)
-        output = seg_query.to(self.dtype)
+        output = seg_query.to(self.dtype).contiguous()
         trace = []
 
         def mask_for(level, out_):
@@ -115,18 +115,18 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             k = F.linear(kins[li], w["x%d.k.w" % i], w["x%d.k.b" % i])
             v = F.linear(srcs[li], w["x%d.v.w" % i], w["x%d.v.b" % i])
             a = kernels.cross_attention(q, k, v, bits, row_open, nh)
-            output = F.layer_norm(output + F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]), (Hd,),
-                                  w["x%d.n.w" % i], w["x%d.n.b" % i])
+            output = kernels.add_layer_norm(output, w["x%d.n.w" % i], w["x%d.n.b" % i],
+                                            r1=F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]))
             # query self-attention (:35-45): q = k = tgt + query_pos, v = tgt
             qk = F.linear(output + qpos, w["s%d.qk.w" % i], w["s%d.qk.b" % i])
             v = F.linear(output, w["s%d.v.w" % i], w["s%d.v.b" % i])
             a = kernels.cross_attention(qk[..., :Hd].contiguous(), qk[..., Hd:].contiguous(), v, None, None, nh, splits=1)
-            output = F.layer_norm(output + F.linear(a, w["s%d.o.w" % i], w["s%d.o.b" % i]), (Hd,),
-                                  w["s%d.n.w" % i], w["s%d.n.b" % i])
+            output = kernels.add_layer_norm(output, w["s%d.n.w" % i], w["s%d.n.b" % i],
+                                            r1=F.linear(a, w["s%d.o.w" % i], w["s%d.o.b" % i]))
             # FFN (:158-162)
             f = F.linear(F.relu(F.linear(output, w["f%d.linear1.w" % i], w["f%d.linear1.b" % i])),
                          w["f%d.linear2.w" % i], w["f%d.linear2.b" % i])
-            output = F.layer_norm(output + f, (Hd,), w["f%d.norm.w" % i], w["f%d.norm.b" % i])
+            output = kernels.add_layer_norm(output, w["f%d.norm.w" % i], w["f%d.norm.b" % i], r1=f)
             if i < cfg.dec_layers - 1:
                 bits, row_open = mask_for((i + 1) % 3, output)
         # final prediction heads (:695-750) — the only ones whose outputs leave the decoder

@@ -55,14 +55,26 @@ class PhiModel:
         kv = None
         if attention_mask is not None:
             kv = attention_mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        h = inputs_embeds
+        h = inputs_embeds.contiguous()
+        a = f = None
         for i in range(cfg.layers):
-            x = F.layer_norm(h, (C,), w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps)
+            if a is None:
+                x = kernels.add_layer_norm(h, w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps)
+            else:  # h = attn + mlp + residual of the previous layer, fused with this layer's input_layernorm
+                h, x = kernels.add_layer_norm(h, w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps, r1=a, r2=f, return_sum=True)
             qkv = F.linear(x, w["%d.qkv.w" % i], w["%d.qkv.b" % i]).view(B, T, 3, nh, hd)
             kernels.rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd)
             a = kernels.causal_attention(qkv, kv, B, T, nh, hd)
             a = F.linear(a, w["%d.dense.w" % i], w["%d.dense.b" % i])
-            f = F.gelu(F.linear(x, w["%d.fc1.w" % i], w["%d.fc1.b" % i]), approximate="tanh")  # gelu_new
+            f = self._fc1_gelu(x, i)
             f = F.linear(f, w["%d.fc2.w" % i], w["%d.fc2.b" % i])
-            h = a + f + h
-        return F.layer_norm(h, (C,), w["fln.w"], w["fln.b"], cfg.eps)
+        return kernels.add_layer_norm(h, w["fln.w"], w["fln.b"], cfg.eps, r1=a, r2=f)
+
+    def _fc1_gelu(self, x, i):
+        """fc1 + gelu_new: bias and tanh-GELU run in the library GEMM's epilogue (cuBLASLt) on the GPU."""
+        w = self.w
+        if x.is_cuda and x.dtype != torch.float32:
+            B, T, C = x.shape
+            y = torch._addmm_activation(w["%d.fc1.b" % i], x.view(B * T, C), w["%d.fc1.w" % i].t(), use_gelu=True)
+            return y.view(B, T, -1)
+        return F.gelu(F.linear(x, w["%d.fc1.w" % i], w["%d.fc1.b" % i]), approximate="tanh")

@@ -103,13 +103,13 @@ class MSDeformAttnPixelDecoder:
         srcs, poss, shapes = [], [], []
         for i, li in enumerate((3, 2, 1)):  # res5, res4, res3 (msdeformattn.py:272-276)
             x = F.linear(toks[li], w["ip%d.w" % i], w["ip%d.b" % i])
-            srcs.append(group_norm_tokens(x, w["ip%d.gw" % i], w["ip%d.gb" % i]))
+            srcs.append(kernels.group_norm_tokens(x, w["ip%d.gw" % i], w["ip%d.gb" % i]))
             H, W = sizes[li]
             shapes.append((H, W))
             pe = position_embedding_sine_tokens(H, W, self.device).to(self.dtype)   # .to(x.dtype) at :276
             poss.append((pe.float() + self.level_embed[i]).to(self.dtype) if self.dtype == torch.float32
                         else (pe + self.level_embed[i].to(self.dtype)))
-        src = torch.cat(srcs, 1)
+        src = torch.cat(srcs, 1).contiguous()
         pos = torch.cat(poss, 0).unsqueeze(0)
         S = src.shape[1]
         starts, acc = [], 0
@@ -124,19 +124,19 @@ class MSDeformAttnPixelDecoder:
             value_hm = value.view(B, S, M, D).permute(0, 2, 1, 3).contiguous()
             a = kernels.timed_msda(kernels.msda_encoder_fused, value_hm, ow.contiguous(), shapes, starts, cfg.enc_points)
             kernels._count()
-            src = F.layer_norm(src + F.linear(a, w["e%d.op.w" % i], w["e%d.op.b" % i]), (cfg.hidden,),
-                               w["e%d.norm1.w" % i], w["e%d.norm1.b" % i])
+            src = kernels.add_layer_norm(src, w["e%d.norm1.w" % i], w["e%d.norm1.b" % i],
+                                         r1=F.linear(a, w["e%d.op.w" % i], w["e%d.op.b" % i]))
             f = F.linear(F.relu(F.linear(src, w["e%d.linear1.w" % i], w["e%d.linear1.b" % i])),
                          w["e%d.linear2.w" % i], w["e%d.linear2.b" % i])
-            src = F.layer_norm(src + f, (cfg.hidden,), w["e%d.norm2.w" % i], w["e%d.norm2.b" % i])
+            src = kernels.add_layer_norm(src, w["e%d.norm2.w" % i], w["e%d.norm2.b" % i], r1=f)
         outs = [t.contiguous() for t in torch.split(src, [h_ * w_ for h_, w_ in shapes], dim=1)]
         # FPN level on res2 (msdeformattn.py:300-309)
         H2, W2 = sizes[0]
-        cur = F.relu(group_norm_tokens(F.linear(toks[0], w["ad.w"], w["ad.b"]), w["ad.gw"], w["ad.gb"]))
+        cur = kernels.group_norm_tokens(F.linear(toks[0], w["ad.w"], w["ad.b"]), w["ad.gw"], w["ad.gb"], relu=True)
         Hl, Wl = shapes[-1]
         up = kernels.bilinear_tokens(outs[-1], Hl, Wl, H2, W2)   # fp32 math, rounded to dtype like `.to(x.dtype)`
         y = (cur + up).view(B, H2, W2, cfg.hidden).permute(0, 3, 1, 2)   # channels-last NCHW view
         y = F.conv2d(y, w["l1.w"], w["l1.b"], padding=1).permute(0, 2, 3, 1).reshape(B, H2 * W2, cfg.hidden)
-        y = F.relu(group_norm_tokens(y, w["l1.gw"], w["l1.gb"]))
+        y = kernels.group_norm_tokens(y.contiguous(), w["l1.gw"], w["l1.gb"], relu=True)
         mask_features = F.linear(y, w["mf.w"], w["mf.b"])
         return mask_features, outs, shapes

@@ -68,22 +68,28 @@ class SwinTransformer:
         x = F.conv2d(x.contiguous(memory_format=torch.channels_last), w["pe.w"], w["pe.b"], stride=ps)
         B, C, Wh, Ww = x.shape
         x = x.permute(0, 2, 3, 1).reshape(B, Wh * Ww, C)
-        x = F.layer_norm(x, (C,), w["pe.nw"], w["pe.nb"])
+        x = kernels.add_layer_norm(x.contiguous(), w["pe.nw"], w["pe.nb"])
         outs, sizes = [], []
         ws = cfg.window
+        LN = kernels.add_layer_norm
         for s, depth in enumerate(cfg.depths):
             nh = cfg.num_heads[s]
+            delta = None   # residual branch not yet added to x (folded into the next fused add + LayerNorm)
             for b in range(depth):
                 p = "layers.%d.blocks.%d." % (s, b)
                 shift = 0 if b % 2 == 0 else ws // 2
-                h = F.layer_norm(x, (C,), w[p + "norm1.w"], w[p + "norm1.b"])
+                if delta is None:
+                    h = LN(x, w[p + "norm1.w"], w[p + "norm1.b"])
+                else:
+                    x, h = LN(x, w[p + "norm1.w"], w[p + "norm1.b"], r1=delta, return_sum=True)
                 qkv = F.linear(h, w[p + "attn.qkv.w"], w[p + "attn.qkv.b"])
                 a = kernels.window_attention(qkv, w[p + "attn.qkv.b"], w[p + "rel"], B, Wh, Ww, C, nh, ws, shift)
-                x = x + F.linear(a, w[p + "attn.proj.w"], w[p + "attn.proj.b"])
-                h = F.layer_norm(x, (C,), w[p + "norm2.w"], w[p + "norm2.b"])
+                a = F.linear(a, w[p + "attn.proj.w"], w[p + "attn.proj.b"])
+                x, h = LN(x, w[p + "norm2.w"], w[p + "norm2.b"], r1=a, return_sum=True)
                 h = F.gelu(F.linear(h, w[p + "mlp.fc1.w"], w[p + "mlp.fc1.b"]))
-                x = x + F.linear(h, w[p + "mlp.fc2.w"], w[p + "mlp.fc2.b"])
-            outs.append(F.layer_norm(x, (C,), w["norm%d.w" % s], w["norm%d.b" % s]))
+                delta = F.linear(h, w[p + "mlp.fc2.w"], w[p + "mlp.fc2.b"])
+            x, out = LN(x, w["norm%d.w" % s], w["norm%d.b" % s], r1=delta, return_sum=True)
+            outs.append(out)
             sizes.append((Wh, Ww))
             if s < len(cfg.depths) - 1:  # PatchMerging swin_trans.py:269-296
                 p = "layers.%d.downsample." % s
@@ -93,7 +99,7 @@ class SwinTransformer:
                 xm = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1)
                 Wh, Ww = (Wh + 1) // 2, (Ww + 1) // 2
                 xm = xm.reshape(B, Wh * Ww, 4 * C)
-                xm = F.layer_norm(xm, (4 * C,), w[p + "norm.w"], w[p + "norm.b"])
+                xm = LN(xm.contiguous(), w[p + "norm.w"], w[p + "norm.b"])
                 x = F.linear(xm, w[p + "red.w"])
                 C = 2 * C
         return outs, sizes

@@ -106,8 +106,27 @@ def msda_encoder_fused(value_hm, ow, spatial_shapes, level_start_index, n_points
     return O.msda_core(value_hm.permute(0, 2, 1, 3).float(), spatial_shapes, loc, aw).to(value_hm.dtype)
 
 
+def add_layer_norm(x, weight, bias, eps=1e-5, r1=None, r2=None, return_sum=False):
+    s = x.float()
+    if r1 is not None:
+        s = s + r1.float()
+    if r2 is not None:
+        s = s + r2.float()
+    if return_sum:
+        s = s.to(x.dtype).float()
+    y = F.layer_norm(s, (x.shape[-1],), weight.float(), bias.float(), eps).to(x.dtype)
+    return (s.to(x.dtype), y) if return_sum else y
+
+
+def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False):
+    y = F.group_norm(x.float().transpose(1, 2), groups, weight.float(), bias.float(), eps).transpose(1, 2)
+    if relu:
+        y = F.relu(y)
+    return y.contiguous().to(x.dtype)
+
+
 def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
-                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused"):
+                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens"):
         monkeypatch.setattr(kernels, name, globals()[name])

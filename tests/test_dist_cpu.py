@@ -1,0 +1,61 @@
+"""N > 1 host path on CPU: world_size-2 gloo processes shard images, gather records, max-reduce times."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from psalm_b200 import dist as PD
+from psalm_b200.structures import Instances
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = PD.shard_indices(5, rank, world)
+    recs = []
+    for i in range(3):   # every rank contributes the same count (weak scaling: fixed per-rank batch)
+        inst = Instances((4, 4))
+        inst.scores = torch.full((7,), float(10 * rank + i))
+        inst.pred_classes = torch.arange(7)
+        inst.pred_masks = torch.ones(7, 4, 4)
+        recs.append(PD.compact_record({"instances": inst}, num_queries=10))
+    allr = PD.gather_records(torch.stack(recs))
+    mx = PD.max_over_ranks([float(rank + 1), 5.0 - rank], "cpu")
+    out_q.put((rank, mine, allr[:, 0, 0].tolist(), allr.shape, mx))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_gather_reduce():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]
+    for r in res:
+        assert r[2] == [0.0, 1.0, 2.0, 10.0, 11.0, 12.0]      # rank order preserved
+        assert tuple(r[3]) == (6, 10, 3)
+        assert r[4] == [2.0, 5.0]                               # max over ranks
+
+
+def test_single_process_passthrough():
+    x = torch.zeros(2, 10, 3)
+    assert PD.gather_records(x) is x
+    assert PD.max_over_ranks([3.0], "cpu") == [3.0]
