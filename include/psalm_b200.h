@@ -128,6 +128,10 @@ int psalm_cross_attention(const void* q, const void* k, const void* v, const uin
  *   psalm_bilinear_tokens: F.interpolate(bilinear, align_corners=False) on token-major maps
  *       [B,Hi,Wi,C] -> [B,Ho,Wo,C]; accumulate != 0 adds into `out` (FPN top-down add, msdeformattn.py:306)
  *   psalm_attn_mask_bits: bits = (logit < 0)  (== sigmoid < 0.5, :757-759), row_open = all blocked */
+/* Intermediate prediction heads in one kernel (16-bit storage, C == 256, Q <= 112): bits = (mask_embed .
+ * feats^T < 0) packed 32 keys / word + row_open; the logits are never written. */
+int psalm_mask_bits_fused(const void* mask_embed, const void* feats, uint32_t* bits, uint8_t* row_open, int B,
+                          int Q, int P, int C, int dtype, void* stream);
 int psalm_mask_logits(const void* mask_embed, const void* feats, void* out, int B, int Q, int P, int C,
                       int dtype, int out_dtype, void* stream);
 int psalm_bilinear_tokens(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int dtype,
@@ -144,10 +148,27 @@ int psalm_add_layernorm(const void* x, const void* r1, const void* r2, const voi
                         void* sum_out, void* y, long long rows, int C, float eps, int dtype, void* stream);
 
 /* GroupNorm (+ optional ReLU) of a token-major map x [B,N,C] (statistics over N x C/groups per group),
- * msdeformattn.py:199-203,244-252.  stats_workspace: 2*B*groups doubles. */
+ * msdeformattn.py:199-203,244-252.  Deterministic (no atomics).
+ * stats_workspace: at least 8 * B * groups * (1 + ceil(N / 256)) bytes. */
 int psalm_groupnorm_tokens(const void* x, const void* weight, const void* bias, void* y,
                            double* stats_workspace, int B, int N, int C, int groups, float eps, int relu,
                            int dtype, void* stream);
+
+/* Fused post-processing of eval_seg (llava_phi.py:1399-1406 up-sampling + the task heads :325-447) for the
+ * common case where the up-sampled map needs no further crop / resize.  Reads the low-resolution mask
+ * logits [Q,H4,W4] and produces, without materialising [Q,H,W] tensors:
+ *   sem_seg    [ncls,H,W] fp32 = softmax(cls)[:, :-1]^T . sigmoid(up(logits))   (probsT_f16: [144,112] fp16,
+ *              class-major, zero padded; NULL together with sem_seg to skip)
+ *   ids / in_mask [H,W]: arg-max_q (wq[q] * sigmoid + negq[q]) and (sigmoid >= 0.5 at the winner)
+ *              (panoptic_inference, llava_phi.py:341-361; NULL x4 to skip)
+ *   inst_masks [K,H,W] fp32 = (up(logits)[slot_query[k]] > 0); slots with query -1 are not written
+ *   partials   [gx*gy, Q, 5] per-CTA sums: count(x>0), sum(sigmoid*[x>0]), count(x>=0), area, inter
+ *              (gx, gy from psalm_postproc_grid); the caller reduces over the first axis. */
+int psalm_postproc_grid(int H, int W, int* gx, int* gy);
+int psalm_postproc_fused(const void* logits, const void* probsT_f16, const float* wq, const float* negq,
+                         const int* slot_query, float* sem_seg, float* inst_masks, int* ids,
+                         unsigned char* in_mask, float* partials, int Q, int H4, int W4, int H, int W, int ncls,
+                         int K, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -114,12 +114,29 @@ __global__ void attn_mask_bits_kernel(const T* __restrict__ logits, uint32_t* __
 
 }  // namespace psalm
 
+namespace psalm {
+int mma_mask_proj(const void* me, const void* feats, void* out, uint32_t* bits, uint8_t* row_open, int B, int Q, int P,
+                  int dtype, cudaStream_t st);
+}
+
 using namespace psalm;
+
+extern "C" int psalm_mask_bits_fused(const void* mask_embed, const void* feats, uint32_t* bits, uint8_t* row_open,
+                                     int B, int Q, int P, int C, int dtype, void* stream) {
+  PSALM_REQUIRE(mask_embed && feats && bits && row_open, "mask_bits_fused: null pointer");
+  if (dtype == PSALM_F32 || C != 256 || Q > 112) {
+    set_error("mask_bits_fused: needs 16-bit storage, C == 256, Q <= 112 (got dtype %d, C %d, Q %d)", dtype, C, Q);
+    return PSALM_E_UNSUPPORTED;
+  }
+  return mma_mask_proj(mask_embed, feats, nullptr, bits, row_open, B, Q, P, dtype, (cudaStream_t)stream);
+}
 
 extern "C" int psalm_mask_logits(const void* mask_embed, const void* feats, void* out, int B, int Q, int P,
                                  int C, int dtype, int out_dtype, void* stream) {
   PSALM_REQUIRE(mask_embed && feats && out, "mask_logits: null pointer");
   PSALM_REQUIRE(out_dtype == dtype || out_dtype == PSALM_F32, "mask_logits: out dtype must be F32 or the input dtype");
+  if (dtype != PSALM_F32 && out_dtype == dtype && C == 256 && Q <= 112 && P % 2 == 0)
+    return mma_mask_proj(mask_embed, feats, out, nullptr, nullptr, B, Q, P, dtype, (cudaStream_t)stream);
   dim3 grid((P + 127) / 128, (Q + 31) / 32, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define ML(T, TO) mask_logits_kernel<T, TO><<<grid, 256, 0, st>>>((const T*)mask_embed, (const T*)feats, (TO*)out, Q, P, C)

@@ -5,9 +5,8 @@
 //                   input_layernorm), the encoder / decoder post-norm layers (msdeformattn.py:59-65,
 //                   mask2former_transformer_decoder.py:42-43,102-103,160-161).  One warp per row,
 //                   the row lives in registers (two-pass mean / variance like ATen), 16-byte accesses.
-//   groupnorm_tokens  GroupNorm(32) on a TOKEN-MAJOR map [B, N, C] (+ optional ReLU): partial
-//                   sum / sum-of-squares per (batch, group) with one atomicAdd(double) per CTA, then a
-//                   streaming apply pass (msdeformattn.py:199-203,244-252 conv+GN(+ReLU) blocks).
+//   groupnorm_tokens  GroupNorm(32) on a TOKEN-MAJOR map [B, N, C] (+ optional ReLU): deterministic
+//                   per-CTA partial sums -> fixed-order finalize (double) -> streaming apply pass (msdeformattn.py:199-203,244-252 conv+GN(+ReLU) blocks).
 #include "common.cuh"
 
 namespace psalm {
@@ -102,19 +101,20 @@ __global__ void __launch_bounds__(128) add_layernorm_kernel(const T* __restrict_
 }
 
 // ---- GroupNorm on token-major maps -----------------------------------------------------------------
-// stats[b, g] = (sum, sumsq) as double; grid = (chunks, B), block 256; C <= 1024, C % (4*groups) == 0
+// Deterministic (no atomics): (1) per-CTA partial (sum, sumsq) per group over a slice of 256 tokens,
+// reduced inside the CTA in a fixed order; (2) a finalize kernel adds the partials of each (batch, group)
+// in a fixed order in double and emits (mean, rstd); (3) streaming apply.
+// C <= 1024, C % (4*groups) == 0, 256 % (C/4) == 0.
 template <typename T>
-__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
-                                                              int N, int C, int groups, int tokens_per_cta) {
-  __shared__ float ssum[64], ssq[64];
+__global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restrict__ x, float2* __restrict__ part,
+                                                                int N, int C, int groups, int tokens_per_cta) {
+  __shared__ float ts[256], tq[256];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * tokens_per_cta;
   const int t1 = min(N, t0 + tokens_per_cta);
   const int cpg = C / groups;
-  if (threadIdx.x < 64) ssum[threadIdx.x] = ssq[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int chunks = C / 4;                         // 4-element chunks per token
-  const int tpb = 256 / chunks > 0 ? 256 / chunks : 1;   // tokens processed concurrently
+  const int chunks = C / 4;                    // 4-element chunks per token
+  const int tpb = 256 / chunks;                // tokens processed concurrently
   const int cidx = threadIdx.x % chunks, trow = threadIdx.x / chunks;
   float s = 0.f, q = 0.f;
   if (trow < tpb) {
@@ -127,39 +127,58 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restric
         q = fmaf(f[i], f[i], q);
       }
     }
-    const int g = (cidx * 4) / cpg;
-    atomicAdd(&ssum[g], s);
-    atomicAdd(&ssq[g], q);
   }
+  ts[threadIdx.x] = s;
+  tq[threadIdx.x] = q;
   __syncthreads();
   if (threadIdx.x < groups) {
-    atomicAdd(&stats[((size_t)b * groups + threadIdx.x) * 2], (double)ssum[threadIdx.x]);
-    atomicAdd(&stats[((size_t)b * groups + threadIdx.x) * 2 + 1], (double)ssq[threadIdx.x]);
+    const int g = threadIdx.x;
+    const int cpgc = cpg / 4;                  // chunks per group
+    float gs = 0.f, gq = 0.f;
+    for (int r = 0; r < tpb; ++r)
+      for (int c = 0; c < cpgc; ++c) {
+        const int t = r * chunks + g * cpgc + c;
+        gs += ts[t];
+        gq += tq[t];
+      }
+    part[((size_t)b * groups + g) * gridDim.x + blockIdx.x] = make_float2(gs, gq);
   }
 }
 
+__global__ void groupnorm_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ mean_rstd, int n_bg,
+                                          int n_part, double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bg) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < n_part; ++k) {
+    const float2 v = part[(size_t)i * n_part + k];
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0) var = 0;
+  mean_rstd[i] = make_float2((float)m, rsqrtf((float)var + eps));
+}
+
 template <typename T>
-__global__ void groupnorm_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats,
+__global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __restrict__ mean_rstd,
                                        const T* __restrict__ w, const T* __restrict__ bias, T* __restrict__ y,
-                                       int B, int N, int C, int groups, float eps, int relu) {
+                                       int B, int N, int C, int groups, int relu) {
   const int cpg = C / groups;
   const long long n4 = (long long)B * N * C / 4;
-  const double cnt = (double)N * cpg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = i * 4;
     const int c = (int)(e % C);
     const int b = (int)(e / ((long long)N * C));
-    const int g = c / cpg;
-    const double m = stats[((size_t)b * groups + g) * 2] / cnt;
-    const double var = stats[((size_t)b * groups + g) * 2 + 1] / cnt - m * m;
-    const float mean = (float)m, rstd = rsqrtf((float)(var > 0 ? var : 0) + eps);
+    const float2 mr = mean_rstd[(size_t)b * groups + c / cpg];
     float f[4], gw[4], gb[4], o[4];
     load4<T>(x + e, f);
     load4<T>(w + c, gw);
     load4<T>(bias + c, gb);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      o[k] = (f[k] - mean) * rstd * gw[k] + gb[k];
+      o[k] = (f[k] - mr.x) * mr.y * gw[k] + gb[k];
       if (relu) o[k] = fmaxf(o[k], 0.f);
     }
     store4<T>(y + e, o);
@@ -186,17 +205,21 @@ static int launch_ln(const void* x, const void* r1, const void* r2, const void* 
 }
 
 template <typename T>
-static int launch_gn(const void* x, const void* w, const void* b, void* y, double* stats, int B, int N, int C,
+static int launch_gn(const void* x, const void* w, const void* b, void* y, double* workspace, int B, int N, int C,
                      int groups, float eps, int relu, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, st);
-  if (e != cudaSuccess) { set_error("groupnorm: memset failed: %s", cudaGetErrorString(e)); return PSALM_E_CUDA; }
   const int tokens_per_cta = 256;
-  dim3 g1((N + tokens_per_cta - 1) / tokens_per_cta, B);
-  groupnorm_stats_kernel<T><<<g1, 256, 0, st>>>((const T*)x, stats, N, C, groups, tokens_per_cta);
+  const int n_part = (N + tokens_per_cta - 1) / tokens_per_cta;
+  float2* mean_rstd = reinterpret_cast<float2*>(workspace);                    // [B*groups]
+  float2* part = mean_rstd + (size_t)B * groups;                               // [B*groups][n_part]
+  dim3 g1(n_part, B);
+  groupnorm_partial_kernel<T><<<g1, 256, 0, st>>>((const T*)x, part, N, C, groups, tokens_per_cta);
+  const int n_bg = B * groups;
+  groupnorm_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(part, mean_rstd, n_bg, n_part,
+                                                              (double)N * (C / groups), eps);
   const long long n4 = (long long)B * N * C / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-  groupnorm_apply_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>((const T*)x, stats, (const T*)w, (const T*)b, (T*)y,
-                                                                     B, N, C, groups, eps, relu);
+  groupnorm_apply_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>((const T*)x, mean_rstd, (const T*)w, (const T*)b,
+                                                                     (T*)y, B, N, C, groups, relu);
   return check_launch("groupnorm_tokens");
 }
 

@@ -1,0 +1,247 @@
+// Fused post-processing of eval_seg (reference language_model/llava_phi.py:1399-1406, 325-447).
+//
+// The reference up-samples the 100 mask-logit maps to [100, H, W] fp32 (419 MB at 1024^2) and then walks
+// that tensor ~a dozen times (sigmoid, semantic einsum, >0 masks, mask scores, panoptic arg-max, areas).
+// Here ONE kernel reads the low-resolution logits [Q, H4, W4] (13-26 MB, L2 resident) and, per tile of
+// 8 x 16 output pixels, produces everything the task heads need:
+//   * x_q = bilinear(logits_q) (F.interpolate align_corners=False semantics), s_q = sigmoid(x_q)
+//   * sem_seg[c, p] = sum_q softmax(cls)[q, c] * s_q          (mma.sync fp16 x fp16 -> fp32, 144x112 x 112x128)
+//   * panoptic arg-max over kept queries of score_q * s_q, and whether s >= 0.5 at the winner
+//   * instance masks [x_q > 0] for the selected (query, class) slots, written in slot order
+//   * per-query partial sums for the mask scores / panoptic areas (deterministic per-CTA partials)
+// The full-resolution [Q, H, W] logits / sigmoid tensors are never materialised.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace psalm {
+
+constexpr int PP_TH = 8, PP_TW = 16, PP_PIX = PP_TH * PP_TW;   // output tile
+constexpr int PP_QP = 112;                                      // queries padded to a multiple of 16
+constexpr int PP_CP = 144;                                      // classes padded to a multiple of 16
+constexpr int PP_SRC_MAX = 64;                                  // source taps per query per tile
+constexpr int PP_BLD = PP_PIX + 8;                              // B operand row stride (halfs)
+constexpr int PP_ALD = PP_QP + 8;                               // A operand row stride (halfs)
+
+__device__ __forceinline__ void pp_ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void pp_ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void pp_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct PostprocArgs {
+  const void* logits;      // [Q, H4, W4]
+  const __half* probsT;    // [PP_CP, PP_QP] fp16, zero padded (class-major), or null
+  const float* wq;         // [Q] keep ? score : 0        (panoptic), or null
+  const float* negq;       // [Q] keep ? 0 : -1
+  const int* slot_query;   // [K] query index of every instance slot (-1 = unused), or null
+  float* sem_seg;          // [ncls, H, W]
+  float* inst_masks;       // [K, H, W]
+  int* ids;                // [H, W]
+  unsigned char* in_mask;  // [H, W]
+  float* partials;         // [n_cta, Q, 5]: pos_cnt, pos_sig, ge_cnt, area, inter
+  int Q, H4, W4, H, W, ncls, K;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* src = reinterpret_cast<float*>(smem_raw);                               // [PP_SRC_MAX][Q pad 104]
+  __half* Bs = reinterpret_cast<__half*>(src + PP_SRC_MAX * 104);               // [PP_QP][PP_BLD]
+  __half* As = Bs + PP_QP * PP_BLD;                                             // [PP_CP][PP_ALD]
+  uint32_t* posbits = reinterpret_cast<uint32_t*>(As + PP_CP * PP_ALD);         // [Q pad 112][4]
+  float* stats = reinterpret_cast<float*>(posbits + PP_QP * 4);                 // [112][5]
+  float* amax_v = stats + PP_QP * 5;                                            // [2][128]
+  int* amax_q = reinterpret_cast<int*>(amax_v + 2 * PP_PIX);                    // [2][128]
+  float* amax_x = reinterpret_cast<float*>(amax_q + 2 * PP_PIX);                // [2][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Q = a.Q;
+  const int ty0 = blockIdx.y * PP_TH, tx0 = blockIdx.x * PP_TW;
+  const float sh = (float)a.H4 / (float)a.H, sw = (float)a.W4 / (float)a.W;
+  // source window of this tile (ATen area_pixel_compute_source_index, align_corners = false)
+  auto srcf = [](float scale, int d) { const float s = scale * ((float)d + 0.5f) - 0.5f; return s < 0.f ? 0.f : s; };
+  const int ylast = min(ty0 + PP_TH, a.H) - 1, xlast = min(tx0 + PP_TW, a.W) - 1;
+  const int sy0 = (int)srcf(sh, ty0), sx0 = (int)srcf(sw, tx0);
+  const int sy1 = min((int)srcf(sh, ylast) + 1, a.H4 - 1), sx1 = min((int)srcf(sw, xlast) + 1, a.W4 - 1);
+  const int SR = sy1 - sy0 + 1, SC = sx1 - sx0 + 1;
+
+  for (int i = tid; i < PP_QP * 5; i += 256) stats[i] = 0.f;
+  for (int i = tid; i < SR * SC * Q; i += 256) {
+    const int q = i / (SR * SC), r = i - q * (SR * SC);
+    const int yy = sy0 + r / SC, xx = sx0 + r % SC;
+    src[r * 104 + q] = to_f32<T>(reinterpret_cast<const T*>(a.logits)[((size_t)q * a.H4 + yy) * a.W4 + xx]);
+  }
+  if (a.probsT)
+    for (int i = tid; i < PP_CP * PP_QP / 8; i += 256) {
+      const int row = i / (PP_QP / 8), c8 = (i % (PP_QP / 8)) * 8;
+      *reinterpret_cast<uint4*>(&As[row * PP_ALD + c8]) = __ldg(reinterpret_cast<const uint4*>(a.probsT + row * PP_QP + c8));
+    }
+  // zero the padded query rows of the B operand
+  for (int i = tid; i < (PP_QP - Q) * PP_BLD; i += 256) Bs[Q * PP_BLD + i] = __float2half(0.f);
+  __syncthreads();
+
+  // ---- phase 1: thread = (pixel p, query parity); x, sigmoid, per-query warp statistics, running arg-max
+  const int p = tid & (PP_PIX - 1), half = tid >> 7;
+  const int py = ty0 + p / PP_TW, px = tx0 + p % PP_TW;
+  const bool inb = py < a.H && px < a.W;
+  const float fy = srcf(sh, py < a.H ? py : a.H - 1), fx = srcf(sw, px < a.W ? px : a.W - 1);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < a.H4 - 1 ? 1 : 0), x1 = x0 + (x0 < a.W4 - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const int o00 = ((y0 - sy0) * SC + (x0 - sx0)) * 104, o01 = ((y0 - sy0) * SC + (x1 - sx0)) * 104;
+  const int o10 = ((y1 - sy0) * SC + (x0 - sx0)) * 104, o11 = ((y1 - sy0) * SC + (x1 - sx0)) * 104;
+  float best_v = -2.f, best_x = 0.f;
+  int best_q = 0;
+  const int wsub = warp & 3;   // which 32-pixel group of the tile this warp covers
+  for (int q = half; q < Q; q += 2) {
+    const float x = hy * (hx * src[o00 + q] + lx * src[o01 + q]) + ly * (hx * src[o10 + q] + lx * src[o11 + q]);
+    const float s = 1.f / (1.f + expf(-x));
+    Bs[q * PP_BLD + p] = __float2half(s);
+    const bool pos = inb && x > 0.f, ge = inb && x >= 0.f;
+    const uint32_t mpos = __ballot_sync(0xffffffffu, pos);
+    const uint32_t mge = __ballot_sync(0xffffffffu, ge);
+    float ps = pos ? s : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    if (lane == 0) {
+      posbits[q * 4 + wsub] = mpos;
+      atomicAdd(&stats[q * 5 + 0], (float)__popc(mpos));
+      atomicAdd(&stats[q * 5 + 1], ps);
+      atomicAdd(&stats[q * 5 + 2], (float)__popc(mge));
+    }
+    if (a.wq) {
+      const float v = fmaf(a.wq[q], s, a.negq[q]);
+      if (v > best_v) { best_v = v; best_q = q; best_x = x; }   // strict >: first maximum wins, like argmax
+    }
+  }
+  if (a.wq) {
+    amax_v[half * PP_PIX + p] = best_v;
+    amax_q[half * PP_PIX + p] = best_q;
+    amax_x[half * PP_PIX + p] = best_x;
+  }
+  __syncthreads();
+  if (a.wq && tid < PP_PIX) {
+    float v0 = amax_v[p], v1 = amax_v[PP_PIX + p];
+    int q0 = amax_q[p], q1 = amax_q[PP_PIX + p];
+    float x0v = amax_x[p], x1v = amax_x[PP_PIX + p];
+    // even queries (half 0) vs odd queries (half 1): lower index wins ties
+    const bool take1 = (v1 > v0) || (v1 == v0 && q1 < q0);
+    const int qb = take1 ? q1 : q0;
+    const float xb = take1 ? x1v : x0v;
+    if (inb) {
+      a.ids[(size_t)py * a.W + px] = qb;
+      const bool im = xb >= 0.f;
+      a.in_mask[(size_t)py * a.W + px] = im ? 1 : 0;
+      atomicAdd(&stats[qb * 5 + 3], 1.f);
+      if (im) atomicAdd(&stats[qb * 5 + 4], 1.f);
+    }
+  }
+  // ---- phase 2: semantic map, D[class, pixel] = probsT[class, q] * sig[q, pixel]
+  if (a.probsT) {
+    float acc[PP_CP / 16][2][4];
+#pragma unroll
+    for (int i = 0; i < PP_CP / 16; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+    const int mi = lane >> 3;
+#pragma unroll
+    for (int ks = 0; ks < PP_QP / 16; ++ks) {
+      uint32_t b[4];   // two 8-pixel n-tiles of this warp's 16 pixels
+      pp_ldsm_x4_t(b, &Bs[(ks * 16 + (lane & 7) + (mi & 1) * 8) * PP_BLD + warp * 16 + (mi >> 1) * 8]);
+#pragma unroll
+      for (int mt = 0; mt < PP_CP / 16; ++mt) {
+        uint32_t af[4];
+        pp_ldsm_x4(af, &As[(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PP_ALD + ks * 16 + (lane >> 4) * 8]);
+        pp_mma(acc[mt][0], af, b[0], b[1]);
+        pp_mma(acc[mt][1], af, b[2], b[3]);
+      }
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < PP_CP / 16; ++mt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int c = mt * 16 + g + r * 8;
+          const int pp = warp * 16 + j * 8 + 2 * t4;
+          const int yy = ty0 + pp / PP_TW, xx = tx0 + pp % PP_TW;
+          if (c < a.ncls && yy < a.H && xx < a.W) {
+            float* dst = a.sem_seg + ((size_t)c * a.H + yy) * a.W + xx;
+            if (xx + 1 < a.W && ((size_t)dst & 7) == 0) *reinterpret_cast<float2*>(dst) = make_float2(acc[mt][j][2 * r], acc[mt][j][2 * r + 1]);
+            else { dst[0] = acc[mt][j][2 * r]; if (xx + 1 < a.W) dst[1] = acc[mt][j][2 * r + 1]; }
+          }
+        }
+  }
+  __syncthreads();
+  // ---- phase 3: instance masks in slot order
+  if (a.slot_query) {
+    for (int k = half; k < a.K; k += 2) {
+      const int q = a.slot_query[k];
+      if (q < 0 || !inb) continue;
+      const bool bit = (posbits[q * 4 + (p >> 5)] >> (p & 31)) & 1u;
+      a.inst_masks[((size_t)k * a.H + py) * a.W + px] = bit ? 1.f : 0.f;
+    }
+  }
+  // ---- per-CTA partial statistics (deterministic final reduction on the host side of the call)
+  float* part = a.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * Q * 5;
+  for (int i = tid; i < Q * 5; i += 256) part[i] = stats[i];
+}
+
+constexpr size_t pp_smem_bytes() {
+  return sizeof(float) * PP_SRC_MAX * 104 + sizeof(__half) * (PP_QP * PP_BLD + PP_CP * PP_ALD) +
+         sizeof(uint32_t) * PP_QP * 4 + sizeof(float) * PP_QP * 5 + (sizeof(float) * 2 + sizeof(int)) * 2 * PP_PIX;
+}
+
+}  // namespace psalm
+
+using namespace psalm;
+
+extern "C" int psalm_postproc_grid(int H, int W, int* gx, int* gy) {
+  *gx = (W + PP_TW - 1) / PP_TW;
+  *gy = (H + PP_TH - 1) / PP_TH;
+  return PSALM_OK;
+}
+
+extern "C" int psalm_postproc_fused(const void* logits, const void* probsT_f16, const float* wq, const float* negq,
+                                    const int* slot_query, float* sem_seg, float* inst_masks, int* ids,
+                                    unsigned char* in_mask, float* partials, int Q, int H4, int W4, int H, int W,
+                                    int ncls, int K, int dtype, void* stream) {
+  PSALM_REQUIRE(logits && partials, "postproc_fused: null pointer");
+  PSALM_REQUIRE(Q > 0 && Q <= 104 && ncls <= PP_CP, "postproc_fused: Q=%d (max 104) / ncls=%d (max %d) unsupported", Q, ncls, PP_CP);
+  PSALM_REQUIRE((probsT_f16 == nullptr) == (sem_seg == nullptr), "postproc_fused: probsT and sem_seg go together");
+  PSALM_REQUIRE((wq == nullptr) == (ids == nullptr) && (wq == nullptr) == (negq == nullptr) && (wq == nullptr) == (in_mask == nullptr),
+                "postproc_fused: wq / negq / ids / in_mask go together");
+  PSALM_REQUIRE((slot_query == nullptr) == (inst_masks == nullptr), "postproc_fused: slot_query and inst_masks go together");
+  // source taps per tile must fit the shared-memory window: (TH*scale + 2) x (TW*scale + 2)
+  const float sh = (float)H4 / (float)H, sw = (float)W4 / (float)W;
+  const int SR = (int)(PP_TH * sh) + 3, SC = (int)(PP_TW * sw) + 3;
+  PSALM_REQUIRE(SR * SC <= PP_SRC_MAX, "postproc_fused: resize factor too small for the fused path (%dx%d source taps per tile)", SR, SC);
+  PostprocArgs a{logits, (const __half*)probsT_f16, wq, negq, slot_query, sem_seg, inst_masks, ids, in_mask, partials,
+                 Q, H4, W4, H, W, ncls, K};
+  dim3 grid((W + PP_TW - 1) / PP_TW, (H + PP_TH - 1) / PP_TH);
+  const size_t smem = pp_smem_bytes();
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+#define PPL(T)                                                                                          \
+  e = cudaFuncSetAttribute(postproc_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e == cudaSuccess) postproc_fused_kernel<T><<<grid, 256, smem, st>>>(a)
+  if (dtype == PSALM_F32) { PPL(float); }
+  else if (dtype == PSALM_F16) { PPL(__half); }
+  else if (dtype == PSALM_BF16) { PPL(__nv_bfloat16); }
+  else { set_error("postproc_fused: unknown dtype %d", dtype); return PSALM_E_ARG; }
+#undef PPL
+  if (e != cudaSuccess) { set_error("postproc_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSALM_E_CUDA; }
+  return check_launch("postproc_fused_kernel");
+}

@@ -189,11 +189,64 @@ def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False):
     for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")):
         _chk(t, "group_norm_tokens." + n)
     B, N, C = x.shape
-    stats = torch.empty(2 * B * groups, dtype=torch.float64, device=x.device)
+    stats = torch.empty(B * groups * (1 + (N + 255) // 256), dtype=torch.float64, device=x.device)
     y = torch.empty_like(x)
     rc = _lib.lib().psalm_groupnorm_tokens(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(stats),
                                            B, N, C, groups, float(eps), 1 if relu else 0,
                                            _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
     _lib.check(rc, "psalm_groupnorm_tokens")
-    _count(2)
+    _count(3)
     return y
+
+
+def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0):
+    """logits [Q,H4,W4] -> dict(sem_seg, ids, in_mask, inst_masks, stats [Q,5]) at output size (H, W).
+    stats columns: count(x>0), sum(sigmoid*[x>0]), count(x>=0), panoptic area, panoptic intersection."""
+    import ctypes
+    _chk(logits, "postproc_fused.logits")
+    Q, H4, W4 = logits.shape
+    dev = logits.device
+    gx, gy = ctypes.c_int(), ctypes.c_int()
+    _lib.lib().psalm_postproc_grid(H, W, ctypes.byref(gx), ctypes.byref(gy))
+    partials = torch.empty((gx.value * gy.value, Q, 5), dtype=torch.float32, device=dev)
+    out = {}
+    sem = ids = inm = inst = None
+    if probsT is not None:
+        _chk(probsT, "postproc_fused.probsT")
+        if probsT.dtype != torch.float16 or tuple(probsT.shape) != (144, 112):
+            raise _lib.PsalmKernelError("postproc_fused: probsT must be fp16 [144,112]")
+        sem = torch.empty((ncls, H, W), dtype=torch.float32, device=dev)
+    if wq is not None:
+        ids = torch.empty((H, W), dtype=torch.int32, device=dev)
+        inm = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    K = 0
+    if slot_query is not None:
+        K = slot_query.shape[0]
+        inst = torch.empty((K, H, W), dtype=torch.float32, device=dev)
+    p = lambda t: _lib.ptr(t) if t is not None else None  # noqa: E731
+    rc = _lib.lib().psalm_postproc_fused(p(logits), p(probsT), p(wq), p(negq), p(slot_query), p(sem), p(inst), p(ids),
+                                         p(inm), p(partials), Q, H4, W4, H, W, ncls, K, _lib.dtype_code(logits.dtype),
+                                         _lib.stream_ptr(dev))
+    _lib.check(rc, "psalm_postproc_fused")
+    _count()
+    out.update(sem_seg=sem, ids=ids, in_mask=inm, inst_masks=inst, stats=partials.sum(0))
+    return out
+
+
+def mask_bits(mask_embed, feats):
+    """Attention mask of the next decoder layer from (mask_embed [B,Q,C], pooled feats [B,P,C]):
+    (bits int32 [B,Q,ceil(P/32)], row_open uint8 [B,Q]).  16-bit storage: one tensor-core kernel that never
+    writes the logits; fp32 storage: exact fp32 projection + threshold kernel."""
+    _chk(mask_embed, "mask_bits.mask_embed")
+    _chk(feats, "mask_bits.feats")
+    B, Q, C = mask_embed.shape
+    P = feats.shape[1]
+    if mask_embed.dtype == torch.float32 or C != 256 or Q > 112:
+        return attn_mask_bits(mask_logits(mask_embed, feats, out_dtype=torch.float32))
+    bits = torch.empty((B, Q, (P + 31) // 32), dtype=torch.int32, device=feats.device)
+    row_open = torch.empty((B, Q), dtype=torch.uint8, device=feats.device)
+    rc = _lib.lib().psalm_mask_bits_fused(_lib.ptr(mask_embed), _lib.ptr(feats), _lib.ptr(bits), _lib.ptr(row_open),
+                                          B, Q, P, C, _lib.dtype_code(feats.dtype), _lib.stream_ptr(feats.device))
+    _lib.check(rc, "psalm_mask_bits_fused")
+    _count(2)
+    return bits, row_open

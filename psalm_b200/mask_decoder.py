@@ -101,11 +101,9 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
 
         def mask_for(level, out_):
             _, me = self._heads_common(out_)
-            lg = kernels.mask_logits(me.contiguous(), pooled[level], out_dtype=torch.float32)
-            bits, row_open = kernels.attn_mask_bits(lg)
             if return_trace:
-                trace.append(lg)
-            return bits, row_open
+                trace.append(kernels.mask_logits(me.contiguous(), pooled[level], out_dtype=torch.float32))
+            return kernels.mask_bits(me.contiguous(), pooled[level])
 
         bits, row_open = mask_for(0, output)
         for i in range(cfg.dec_layers):

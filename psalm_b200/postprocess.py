@@ -129,3 +129,95 @@ def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8, 
     lut = torch.from_numpy(seg_of_query).to(cls.device)
     pan = torch.where(in_mask, lut[ids], torch.zeros((), dtype=torch.int32, device=cls.device))
     return pan.view(H, W).to(torch.int32), info
+
+
+def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_list=None, semantic_on=False,
+                      instance_on=False, panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8, ovl_thr=0.8):
+    """All task heads of one image from the LOW-RESOLUTION mask logits [Q,H4,W4] with one fused kernel
+    (csrc/postproc.cu) — same results as the functions above applied to the up-sampled [Q,H,W] map, which
+    is never materialised.  Small [Q, n_cls] tensor algebra stays in torch; ONE D2H copy carries what the
+    host-side panoptic merge and the instance count need."""
+    Q = logits.shape[0]
+    dev = logits.device
+    probsT = wq = negq = slots = None
+    ncls = 0
+    r = {}
+    if cls is not None:
+        probs_full = F.softmax(cls.float(), dim=-1)
+        probs = probs_full[:, :-1]
+        ncls = probs.shape[1]
+    if semantic_on:
+        probsT = torch.zeros((144, 112), dtype=torch.float16, device=dev)
+        probsT[:ncls, :Q] = probs.t().to(torch.float16)
+    if panoptic_on:
+        scores, labels = probs_full.max(-1)
+        keep = labels.ne(ncls) & (scores > obj_thr)
+        wq = torch.where(keep, scores, torch.zeros_like(scores)).contiguous()
+        negq = (keep.float() - 1.0).contiguous()
+    if instance_on:
+        s, idx = probs.flatten(0, 1).topk(topk, sorted=False)
+        lab, qi = idx % ncls, idx // ncls
+        if panoptic_on:
+            thing = torch.as_tensor([bool(t) for t in is_thing_list], device=dev)
+            keep_i = thing[lab]
+            order = torch.sort((~keep_i).to(torch.uint8), stable=True).indices      # kept slots first
+            s, lab, qi, keep_i = s[order], lab[order], qi[order], keep_i[order]
+        else:
+            keep_i = torch.ones_like(qi, dtype=torch.bool)
+        slots = torch.where(keep_i, qi, torch.full_like(qi, -1)).to(torch.int32).contiguous()
+    elif referring_on:
+        s, qi = torch.sigmoid(SEG_cls.float()).flatten(0, 1).topk(topk, sorted=False)
+        keep_i = torch.ones_like(qi, dtype=torch.bool)
+        lab = None
+        slots = qi.to(torch.int32).contiguous()
+    k = kernels.postproc_fused(logits.contiguous(), H, W, probsT, wq, negq, slots, ncls)
+    st = k["stats"]
+    if semantic_on:
+        r["sem_seg"] = k["sem_seg"]
+    n_inst = None
+    host_rows = []
+    if slots is not None:
+        host_rows.append(keep_i.sum().view(1).float())
+    if panoptic_on:
+        host_rows += [keep.float(), labels.float(), st[:, 3], st[:, 2], st[:, 4]]
+    host = torch.cat(host_rows).cpu().numpy() if host_rows else None        # the one D2H copy
+    pos = 0
+    if slots is not None:
+        n_inst = int(host[0])
+        pos = 1
+        ms = st[:, 1] / (st[:, 0] + 1e-6)                                   # per-query mask score
+        inst = Instances((H, W))
+        inst.pred_masks = k["inst_masks"][:n_inst]
+        inst.pred_boxes = Boxes(torch.zeros(n_inst, 4))
+        inst.scores = (s * ms[qi])[:n_inst]
+        if lab is not None:
+            inst.pred_classes = lab[:n_inst]
+        inst.query_index = qi[:n_inst]
+        r["instances"] = inst
+    if panoptic_on:
+        hk = host[pos:].reshape(5, Q)
+        seg_of_query = np.zeros(Q, np.int32)
+        info, stuff, cur = [], {}, 0
+        for q in range(Q):
+            if not hk[0, q]:
+                continue
+            pc, a, o, it = int(hk[1, q]), int(hk[2, q]), int(hk[3, q]), int(hk[4, q])
+            if a > 0 and o > 0 and it > 0:
+                if a / o < ovl_thr:
+                    continue
+                isthing = bool(is_thing_list[pc])
+                if not isthing:
+                    if pc in stuff:
+                        seg_of_query[q] = stuff[pc]
+                        continue
+                    stuff[pc] = cur + 1
+                cur += 1
+                seg_of_query[q] = cur
+                info.append(dict(id=cur, isthing=isthing, category_id=pc))
+        if hk[0].sum() == 0:
+            pan = torch.zeros((H, W), dtype=torch.int32, device=dev)
+        else:
+            lut = torch.from_numpy(seg_of_query).to(dev)
+            pan = torch.where(k["in_mask"].bool(), lut[k["ids"].long()], torch.zeros((), dtype=torch.int32, device=dev))
+        r["panoptic_seg"] = (pan.to(torch.int32), info)
+    return r

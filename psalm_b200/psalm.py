@@ -50,6 +50,8 @@ class PSALM:
                  seg_task="panoptic", use_cuda_graph=False):
         self._check_runtime(device)
         self.use_cuda_graph = use_cuda_graph
+        # one fused kernel for the task heads (16-bit storage); fp32 parity runs keep the exact torch path
+        self.fused_postprocess = dtype != torch.float32
         if dtype == torch.float32:  # true fp32 for parity runs (cuDNN would otherwise pick TF32)
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
@@ -203,12 +205,25 @@ class PSALM:
         H4, W4 = out["mask_size"]
         B, Q = out["pred_masks"].shape[:2]
         pm = out["pred_masks"].view(B, Q, H4, W4)
-        mask_pred = F.interpolate(pm.float(), size=(Hp, Wp), mode="bilinear", align_corners=False)
+        mask_pred = None
         results = []
         for b in range(B):
             info = seg_info[b]
             height, width = info.get("height", Hi), info.get("width", Wi)
             oh, ow = PP.unpadded_box(info["padding_mask"])
+            cls_b = out["pred_class_name_logits"][b] if out["pred_class_name_logits"] is not None else None
+            seg_b = out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None
+            trivial = (oh, ow) == (Hp, Wp) and (height, width) == (Hp, Wp)
+            if self.fused_postprocess and trivial and Hp >= 2 * H4 and Wp >= 2 * W4 and Q <= 104 and \
+                    (cls_b is None or cls_b.shape[-1] - 1 <= 144):
+                from . import kernels
+                results.append(PP.fused_postprocess(
+                    kernels, pm[b], Hp, Wp, cls_b, seg_b, getattr(self, "is_thing_list", None), self.semantic_on,
+                    self.instance_on, self.panoptic_on, self.referring_on, self.test_topk_per_image,
+                    self.cfg.mask.object_mask_threshold, self.cfg.mask.overlap_threshold))
+                continue
+            if mask_pred is None:
+                mask_pred = F.interpolate(pm.float(), size=(Hp, Wp), mode="bilinear", align_corners=False)
             mp = mask_pred[b]
             r = {}
             if self.sem_seg_postprocess_before_inference:

@@ -125,8 +125,40 @@ def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False):
     return y.contiguous().to(x.dtype)
 
 
+def mask_bits(mask_embed, feats):
+    return attn_mask_bits(mask_logits(mask_embed, feats, torch.float32))
+
+
 def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
-                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens"):
+                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits"):
         monkeypatch.setattr(kernels, name, globals()[name])
+
+
+def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0):
+    """torch restatement of csrc/postproc.cu (one tile = the whole image)."""
+    Q = logits.shape[0]
+    x = F.interpolate(logits.float()[None], size=(H, W), mode="bilinear", align_corners=False)[0]
+    s = torch.sigmoid(x)
+    out = dict(sem_seg=None, ids=None, in_mask=None, inst_masks=None)
+    stats = torch.zeros(Q, 5)
+    stats[:, 0] = (x > 0).flatten(1).sum(1)
+    stats[:, 1] = (s * (x > 0)).flatten(1).sum(1)
+    stats[:, 2] = (x >= 0).flatten(1).sum(1)
+    if probsT is not None:
+        out["sem_seg"] = torch.einsum("cq,qhw->chw", probsT[:ncls, :Q].float(), s.half().float())
+    if wq is not None:
+        ids = (wq.view(-1, 1, 1) * s + negq.view(-1, 1, 1)).argmax(0)
+        inm = x.flatten(1).gather(0, ids.view(1, -1)).view(H, W) >= 0
+        stats[:, 3] = torch.bincount(ids.view(-1), minlength=Q)
+        stats[:, 4] = torch.bincount(ids.view(-1), weights=inm.view(-1).float(), minlength=Q)
+        out["ids"], out["in_mask"] = ids.to(torch.int32), inm.to(torch.uint8)
+    if slot_query is not None:
+        m = torch.zeros(slot_query.shape[0], H, W)
+        for k, q in enumerate(slot_query.tolist()):
+            if q >= 0:
+                m[k] = (x[q] > 0).float()
+        out["inst_masks"] = m
+    out["stats"] = stats
+    return out

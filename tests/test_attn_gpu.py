@@ -120,3 +120,35 @@ def test_pooled_mask_equals_reference_order():
         got = kernels.mask_logits(me, pooled, out_dtype=torch.float32) < 0
         flips = (ref != got).float().mean().item()
         assert flips < 1e-4, flips
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("P", [1024, 389, 4096 + 32])
+def test_mask_bits_fused_and_mma_logits(dt, P, attn_impl):
+    """Tensor-core mask projection: final logits equal the fp32 restatement within storage rounding; the
+    fused bit mask equals thresholding those logits except where |logit| is at rounding level."""
+    if attn_impl == "simt":
+        pytest.skip("independent of the attention implementation switch")
+    torch.manual_seed(P)
+    B, Q, C = 2, 100, 256
+    me = torch.randn(B, Q, C).to(DT[dt])
+    f = torch.randn(B, P, C).to(DT[dt])
+    ref = emu.mask_logits(me.float(), f.float(), torch.float32)
+    if P % 2 == 0:
+        out = kernels.mask_logits(me.cuda(), f.cuda())
+        _close(out, ref, dt)
+    bits, ro = kernels.mask_bits(me.cuda(), f.cuda())
+    ref_bits, ref_ro = emu.attn_mask_bits(ref)
+    got = ((bits.cpu().long() & 0xFFFFFFFF).unsqueeze(-1) >> torch.arange(32)) & 1
+    want = ((ref_bits.long() & 0xFFFFFFFF).unsqueeze(-1) >> torch.arange(32)) & 1
+    mism = (got != want).view(B, Q, -1)[..., :P]
+    assert (mism & (ref.abs() > 1e-3)).sum() == 0      # flips only where the fp32 logit is ~0
+    assert mism.float().mean() < 1e-4
+    assert torch.equal(ro.cpu(), ref_ro)
+    f2 = f.clone()
+    me2 = me.clone()
+    me2[0, 5] = 0
+    me2[0, 5, 0] = 1.0
+    f2[0, :, 0] = -1.0          # row 5 of batch 0: every key blocked -> row_open
+    _, ro2 = kernels.mask_bits(me2.cuda(), f2.cuda())
+    assert int(ro2[0, 5]) == 1
