@@ -322,7 +322,7 @@ __global__ void flash_combine_kernel(Policy pol, AttnDims dm, const float* __res
 // Swin window kernel: grid = (B*nW, nh), block = 288 (9 warps), N = 144 tokens, head_dim 32
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(288) window_mma_kernel(const T* __restrict__ qkv, const T* __restrict__ qkv_bias,
+__global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict__ qkv, const T* __restrict__ qkv_bias,
                                                          const float* __restrict__ rel, T* __restrict__ out,
                                                          int H, int W, int Hp, int Wp, int shift, int nh, int C,
                                                          int nWx, int nW) {
@@ -459,6 +459,14 @@ static int launch_flash(const Policy& pol, AttnDims dm, int hd, float* workspace
   dim3 grid(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
   PSALM_REQUIRE(dm.H <= 65535 && dm.B <= 65535, "%s: grid too large", what);
   PSALM_REQUIRE(dm.splits == 1 || workspace != nullptr, "%s: split-K needs a workspace", what);
+  static bool carveout_set = false;   // per (T, Policy) instantiation
+  if (!carveout_set) {
+    // 4 CTAs x 46 KB (HD = 64) per SM only fit if the L1/shared split favours shared memory; the driver's
+    // default carve-out left ONE CTA (4 warps) per SM (ncu: profiles/r1c_window_mma_ncu_details.txt)
+    cudaFuncSetAttribute(flash_mma_kernel<T, 32, Policy>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(flash_mma_kernel<T, 64, Policy>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    carveout_set = true;
+  }
   if (hd == 32) {
     flash_mma_kernel<T, 32, Policy><<<grid, 128, 0, st>>>(pol, dm, workspace);
     if (dm.splits > 1) flash_combine_kernel<Policy, 32><<<148 * 2, 256, 0, st>>>(pol, dm, workspace);
@@ -504,6 +512,12 @@ int mma_window_attention(const void* qkv, const void* qkv_bias, const float* rel
   const int nWx = Wp / ws, nW = nWx * (Hp / ws);
   dim3 grid(B * nW, nh);
   PSALM_REQUIRE(nh <= 65535, "window_attention: too many heads");
+  static bool carveout_set = false;
+  if (!carveout_set) {  // two 35 KB CTAs per SM need more than the default shared-memory carve-out
+    cudaFuncSetAttribute(window_mma_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(window_mma_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    carveout_set = true;
+  }
   if (dtype == PSALM_BF16)
     window_mma_kernel<__nv_bfloat16><<<grid, 288, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_bias, rel,
                                                           (__nv_bfloat16*)out, H, W, Hp, Wp, shift, nh, C, nWx, nW);

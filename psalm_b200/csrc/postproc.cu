@@ -20,6 +20,7 @@ constexpr int PP_TH = 8, PP_TW = 16, PP_PIX = PP_TH * PP_TW;   // output tile
 constexpr int PP_QP = 112;                                      // queries padded to a multiple of 16
 constexpr int PP_CP = 144;                                      // classes padded to a multiple of 16
 constexpr int PP_SRC_MAX = 64;                                  // source taps per query per tile
+constexpr int PP_SLD = 105;                                     // source row stride (odd: conflict-free)
 constexpr int PP_BLD = PP_PIX + 8;                              // B operand row stride (halfs)
 constexpr int PP_ALD = PP_QP + 8;                               // A operand row stride (halfs)
 
@@ -56,11 +57,12 @@ struct PostprocArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* src = reinterpret_cast<float*>(smem_raw);                               // [PP_SRC_MAX][Q pad 104]
-  __half* Bs = reinterpret_cast<__half*>(src + PP_SRC_MAX * 104);               // [PP_QP][PP_BLD]
+  float* src = reinterpret_cast<float*>(smem_raw);                               // [PP_SRC_MAX][PP_SLD]
+  __half* Bs = reinterpret_cast<__half*>(src + PP_SRC_MAX * PP_SLD);             // [PP_QP][PP_BLD] (64*105*4 B is a multiple of 16)
   __half* As = Bs + PP_QP * PP_BLD;                                             // [PP_CP][PP_ALD]
-  uint32_t* posbits = reinterpret_cast<uint32_t*>(As + PP_CP * PP_ALD);         // [Q pad 112][4]
-  float* stats = reinterpret_cast<float*>(posbits + PP_QP * 4);                 // [112][5]
+  uint32_t* posbits = reinterpret_cast<uint32_t*>(As + PP_CP * PP_ALD);         // [Q pad 112][4]  x > 0
+  uint32_t* gebits = posbits + PP_QP * 4;                                       // [Q pad 112][4]  x >= 0
+  float* stats = reinterpret_cast<float*>(gebits + PP_QP * 4);                  // [112][5]
   float* amax_v = stats + PP_QP * 5;                                            // [2][128]
   int* amax_q = reinterpret_cast<int*>(amax_v + 2 * PP_PIX);                    // [2][128]
   float* amax_x = reinterpret_cast<float*>(amax_q + 2 * PP_PIX);                // [2][128]
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
   for (int i = tid; i < SR * SC * Q; i += 256) {
     const int q = i / (SR * SC), r = i - q * (SR * SC);
     const int yy = sy0 + r / SC, xx = sx0 + r % SC;
-    src[r * 104 + q] = to_f32<T>(reinterpret_cast<const T*>(a.logits)[((size_t)q * a.H4 + yy) * a.W4 + xx]);
+    src[r * PP_SLD + q] = to_f32<T>(reinterpret_cast<const T*>(a.logits)[((size_t)q * a.H4 + yy) * a.W4 + xx]);
   }
   if (a.probsT)
     for (int i = tid; i < PP_CP * PP_QP / 8; i += 256) {
@@ -99,29 +101,25 @@ __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = y0 + (y0 < a.H4 - 1 ? 1 : 0), x1 = x0 + (x0 < a.W4 - 1 ? 1 : 0);
   const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-  const int o00 = ((y0 - sy0) * SC + (x0 - sx0)) * 104, o01 = ((y0 - sy0) * SC + (x1 - sx0)) * 104;
-  const int o10 = ((y1 - sy0) * SC + (x0 - sx0)) * 104, o11 = ((y1 - sy0) * SC + (x1 - sx0)) * 104;
+  const int o00 = ((y0 - sy0) * SC + (x0 - sx0)) * PP_SLD, o01 = ((y0 - sy0) * SC + (x1 - sx0)) * PP_SLD;
+  const int o10 = ((y1 - sy0) * SC + (x0 - sx0)) * PP_SLD, o11 = ((y1 - sy0) * SC + (x1 - sx0)) * PP_SLD;
   float best_v = -2.f, best_x = 0.f;
   int best_q = 0;
   const int wsub = warp & 3;   // which 32-pixel group of the tile this warp covers
+  const float* wqp = a.wq;
+  const float* ngp = a.negq;
   for (int q = half; q < Q; q += 2) {
     const float x = hy * (hx * src[o00 + q] + lx * src[o01 + q]) + ly * (hx * src[o10 + q] + lx * src[o11 + q]);
-    const float s = 1.f / (1.f + expf(-x));
+    const float s = __fdividef(1.f, 1.f + __expf(-x));
     Bs[q * PP_BLD + p] = __float2half(s);
-    const bool pos = inb && x > 0.f, ge = inb && x >= 0.f;
-    const uint32_t mpos = __ballot_sync(0xffffffffu, pos);
-    const uint32_t mge = __ballot_sync(0xffffffffu, ge);
-    float ps = pos ? s : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    const uint32_t mpos = __ballot_sync(0xffffffffu, inb && x > 0.f);
+    const uint32_t mge = __ballot_sync(0xffffffffu, inb && x >= 0.f);
     if (lane == 0) {
       posbits[q * 4 + wsub] = mpos;
-      atomicAdd(&stats[q * 5 + 0], (float)__popc(mpos));
-      atomicAdd(&stats[q * 5 + 1], ps);
-      atomicAdd(&stats[q * 5 + 2], (float)__popc(mge));
+      gebits[q * 4 + wsub] = mge;
     }
-    if (a.wq) {
-      const float v = fmaf(a.wq[q], s, a.negq[q]);
+    if (wqp) {
+      const float v = fmaf(__ldg(wqp + q), s, __ldg(ngp + q));
       if (v > best_v) { best_v = v; best_q = q; best_x = x; }   // strict >: first maximum wins, like argmax
     }
   }
@@ -131,6 +129,26 @@ __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
     amax_x[half * PP_PIX + p] = best_x;
   }
   __syncthreads();
+  if (tid >= 128 && tid - 128 < Q) {   // per-query statistics of this tile (second half of the CTA; first half does the arg-max)
+    const int q = tid - 128;
+    float cnt = 0.f, gcnt = 0.f, ps = 0.f;
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+      const uint32_t m = posbits[q * 4 + wd];
+      cnt += (float)__popc(m);
+      gcnt += (float)__popc(gebits[q * 4 + wd]);
+      const __half2* row = reinterpret_cast<const __half2*>(&Bs[q * PP_BLD + wd * 32]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 f = __half22float2(row[i]);
+        ps += ((m >> (2 * i)) & 1u) ? f.x : 0.f;
+        ps += ((m >> (2 * i + 1)) & 1u) ? f.y : 0.f;
+      }
+    }
+    stats[q * 5 + 0] = cnt;
+    stats[q * 5 + 1] = ps;
+    stats[q * 5 + 2] = gcnt;
+  }
   if (a.wq && tid < PP_PIX) {
     float v0 = amax_v[p], v1 = amax_v[PP_PIX + p];
     int q0 = amax_q[p], q1 = amax_q[PP_PIX + p];
@@ -200,8 +218,8 @@ __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
 }
 
 constexpr size_t pp_smem_bytes() {
-  return sizeof(float) * PP_SRC_MAX * 104 + sizeof(__half) * (PP_QP * PP_BLD + PP_CP * PP_ALD) +
-         sizeof(uint32_t) * PP_QP * 4 + sizeof(float) * PP_QP * 5 + (sizeof(float) * 2 + sizeof(int)) * 2 * PP_PIX;
+  return sizeof(float) * (PP_SRC_MAX * PP_SLD) + sizeof(__half) * (PP_QP * PP_BLD + PP_CP * PP_ALD) +
+         sizeof(uint32_t) * PP_QP * 8 + sizeof(float) * PP_QP * 5 + (sizeof(float) * 2 + sizeof(int)) * 2 * PP_PIX;
 }
 
 }  // namespace psalm

@@ -182,6 +182,31 @@ class PSALM:
         return SEQ.build_plan(input_ids, attention_mask, n_img, self.num_queries, class_name_ids, cls_indices,
                               class_name_embedding_indices, token_refer_id, refer_embedding_indices)
 
+    def _cached_plan(self, input_ids, attention_mask, image_hw, class_name_ids, cls_indices,
+                     class_name_embedding_indices, token_refer_id, refer_embedding_indices):
+        """The sequence plan depends only on the prompt (ids / masks / class-name tables) and the image size;
+        evaluation loops reuse one prompt for every image, so the device-resident plan is cached by content."""
+        def key_of(t):
+            if t is None:
+                return None
+            if isinstance(t, (list, tuple)):
+                return tuple(key_of(x) for x in t)
+            t = t.detach().cpu().contiguous()
+            return (tuple(t.shape), str(t.dtype), t.numpy().tobytes())
+        key = (tuple(image_hw),) + tuple(key_of(t) for t in (input_ids, attention_mask, class_name_ids, cls_indices,
+                                                              class_name_embedding_indices, token_refer_id,
+                                                              refer_embedding_indices))
+        if not hasattr(self, "_plans"):
+            self._plans = {}
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 16:
+                self._plans.pop(next(iter(self._plans)))
+            plan = self.make_plan(input_ids, attention_mask, image_hw, class_name_ids, cls_indices,
+                                  class_name_embedding_indices, token_refer_id, refer_embedding_indices).to(self.device)
+            self._plans[key] = plan
+        return plan
+
     @torch.no_grad()
     def eval_seg(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
                  use_cache=None, output_attentions=None, output_hidden_states=None, images=None, return_dict=None,
@@ -191,8 +216,8 @@ class PSALM:
             assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
             self.is_thing_list = is_thing_list
         images_d = images.to(self.device, non_blocking=True)
-        plan = self.make_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
-                              class_name_embedding_indices, token_refer_id, refer_embedding_indices).to(self.device)
+        plan = self._cached_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
+                                 class_name_embedding_indices, token_refer_id, refer_embedding_indices)
         out = self.forward_core_graphed(images_d, plan) if self.use_cuda_graph else self.forward_core(images_d, plan)
         return self.post_process(out, images.shape[-2:], seg_info)
 
