@@ -73,10 +73,14 @@ struct CausalMma {
   __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
     return ldg16(ptr(which, b, h, n, d0));
   }
-  __device__ __forceinline__ float score(int b, int h, int qi, int kj, float s) const {
-    if (kj > qi) return -INFINITY;
-    if (key_valid && !key_valid[(size_t)b * T_ + kj]) return -INFINITY;
-    return s;
+  // bit j set = key (kt*64 + j) is blocked for query row qi; kv = packed invalid-key bits of this tile
+  __device__ __forceinline__ unsigned long long blocked(int b, int qi, int kt, unsigned long long kv) const {
+    const int d = qi - kt * 64;   // keys with j > d are in the future
+    const unsigned long long m = d >= 63 ? 0ull : (d < 0 ? ~0ull : (~0ull << (d + 1)));
+    return m | kv;
+  }
+  __device__ __forceinline__ bool key_invalid(int b, int kj) const {
+    return key_valid && !key_valid[(size_t)b * T_ + kj];
   }
   __device__ __forceinline__ void store2(int b, int h, int n, int d, float v0, float v1) const {
     *reinterpret_cast<uint32_t*>(out + ((size_t)b * T_ + n) * nh * hd + h * hd + d) = pack2<T>(v0, v1);
@@ -102,13 +106,15 @@ struct CrossMma {
   __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
     return ldg16(ptr(which, b, h, n, d0));
   }
-  __device__ __forceinline__ float score(int b, int h, int qi, int kj, float s) const {
-    if (bits) {
-      const size_t row = (size_t)b * Lq + qi;
-      if (!(row_open && row_open[row]) && ((__ldg(bits + row * W32 + (kj >> 5)) >> (kj & 31)) & 1u)) return -INFINITY;
-    }
-    return s;
+  __device__ __forceinline__ unsigned long long blocked(int b, int qi, int kt, unsigned long long kv) const {
+    if (!bits || qi >= Lq) return kv;
+    const size_t row = (size_t)b * Lq + qi;
+    if (row_open && row_open[row]) return kv;
+    const uint32_t w0 = 2 * kt < W32 ? __ldg(bits + row * W32 + 2 * kt) : 0u;
+    const uint32_t w1 = 2 * kt + 1 < W32 ? __ldg(bits + row * W32 + 2 * kt + 1) : 0u;
+    return ((unsigned long long)w1 << 32 | w0) | kv;
   }
+  __device__ __forceinline__ bool key_invalid(int b, int kj) const { return false; }
   __device__ __forceinline__ void store2(int b, int h, int n, int d, float v0, float v1) const {
     *reinterpret_cast<uint32_t*>(out + ((size_t)b * Lq + n) * nh * hd + h * hd + d) = pack2<T>(v0, v1);
   }
@@ -125,6 +131,7 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
   constexpr int BQ = 64, BK = 64, LD = HD + 8;
   __shared__ __align__(16) T Qs[BQ * LD];
   __shared__ __align__(16) T KVs[2][2][BK * LD];   // [stage][K|V]
+  __shared__ unsigned long long kvbits[128];       // per key tile: keys beyond Lk / padded keys (bit = blocked)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   // heavy (late, causal) query tiles first: better tail balance
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
-  const float sc = dm.scale;
+  const float sc = dm.scale * kLog2e;   // scores are tracked in the log2 domain
 
   auto prefetch = [&](int kt, int stage) {
     for (int i = tid; i < BK * HD / 8; i += 128) {
@@ -171,6 +178,14 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
     }
     cp_async_commit();
   };
+  for (int t = kt0 + tid; t < kt1; t += 128) {
+    unsigned long long m = 0ull;
+    for (int j = 0; j < BK; ++j) {
+      const int kj = t * BK + j;
+      if (kj >= dm.Lk || pol.key_invalid(b, kj)) m |= 1ull << j;
+    }
+    kvbits[t - kt0] = m;
+  }
   if (kt0 < kt1) prefetch(kt0, 0);
   for (int kt = kt0; kt < kt1; ++kt) {
     const int stage = (kt - kt0) & 1;
@@ -197,27 +212,42 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
         mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
       }
     }
-    // ---- scale, policy mask, online softmax (log2 domain)
+    // ---- masks (bit tests against per-row 64-key masks; skipped when the whole tile is open),
+    //      online softmax in the log2 domain
+    const unsigned long long kv = kvbits[kt - kt0];
+    const unsigned long long bm0 = pol.blocked(b, r0, kt, kv) >> (2 * t4);
+    const unsigned long long bm1 = pol.blocked(b, r1, kt, kv) >> (2 * t4);
+    const bool any_blocked = __any_sync(0xffffffffu, (bm0 | bm1) != 0ull);
     float tmax[2] = {-INFINITY, -INFINITY};
+    if (!any_blocked) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int qi = (e < 2) ? r0 : r1;
-        const int kj = kt * BK + nt * 8 + 2 * t4 + (e & 1);
-        float v = -INFINITY;
-        if (qi < dm.Lq && kj < dm.Lk) v = pol.score(b, h, qi, kj, s[nt][e] * sc) * kLog2e;
-        s[nt][e] = v;
-        tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+        for (int e = 0; e < 4; ++e) {
+          s[nt][e] *= sc;
+          tmax[e >> 1] = fmaxf(tmax[e >> 1], s[nt][e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned long long bm = (e < 2) ? bm0 : bm1;
+          const bool blk = (bm >> (nt * 8 + (e & 1))) & 1ull;
+          s[nt][e] = blk ? -INFINITY : s[nt][e] * sc;
+          tmax[e >> 1] = fmaxf(tmax[e >> 1], s[nt][e]);
+        }
       }
     }
-    float corr[2];
+    float corr[2], msub[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
       const float m_new = fmaxf(m_run[r], tmax[r]);
-      corr[r] = (m_new == -INFINITY || m_run[r] == -INFINITY) ? (m_new == -INFINITY ? 1.f : 0.f) : exp2f(m_run[r] - m_new);
+      corr[r] = (m_new == -INFINITY) ? 1.f : exp2f(m_run[r] - m_new);   // exp2f(-inf) = 0 for the first tile
+      msub[r] = (m_new == -INFINITY) ? 0.f : m_new;                     // avoids (-inf) - (-inf)
       m_run[r] = m_new;
     }
     float psum[2] = {0.f, 0.f};
@@ -225,10 +255,9 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int r = e >> 1;
-        const float p = (s[nt][e] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_run[r]);
+        const float p = exp2f(s[nt][e] - msub[e >> 1]);   // blocked: exp2f(-inf) = 0
         s[nt][e] = p;
-        psum[r] += p;
+        psum[e >> 1] += p;
       }
     }
 #pragma unroll
@@ -321,20 +350,22 @@ __global__ void flash_combine_kernel(Policy pol, AttnDims dm, const float* __res
 // ------------------------------------------------------------------------------------------------
 // Swin window kernel: grid = (B*nW, nh), block = 288 (9 warps), N = 144 tokens, head_dim 32
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int HPC>
 __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict__ qkv, const T* __restrict__ qkv_bias,
-                                                         const float* __restrict__ rel, T* __restrict__ out,
-                                                         int H, int W, int Hp, int Wp, int shift, int nh, int C,
-                                                         int nWx, int nW) {
+                                                            const float* __restrict__ rel, T* __restrict__ out,
+                                                            int H, int W, int Hp, int Wp, int shift, int nh, int C,
+                                                            int nWx, int nW) {
+  // One CTA = one window x HPC consecutive heads; the Q/K/V tiles of head i+1 stream in with cp.async
+  // while head i is computed (the un-pipelined version spent 30 % of its stall samples waiting on the
+  // tile fill, profiles/r1c_window_mma_ncu_details.txt).
   constexpr int N = 144, WS = 12, HD = 32, LD = HD + 8;
-  __shared__ __align__(16) T Qs[N * LD];
-  __shared__ __align__(16) T Ks[N * LD];
-  __shared__ __align__(16) T Vs[N * LD];
-  __shared__ int tok[N];
-  __shared__ unsigned char reg[N];
+  extern __shared__ __align__(16) unsigned char win_smem[];
+  T* bufs = reinterpret_cast<T*>(win_smem);                     // [2 stages][3: q,k,v][N * LD]
+  int* tok = reinterpret_cast<int*>(bufs + 2 * 3 * N * LD);     // [N]
+  unsigned char* reg = reinterpret_cast<unsigned char*>(tok + N);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int z = blockIdx.x, h = blockIdx.y;
+  const int z = blockIdx.x, h0 = blockIdx.y * HPC;
   if (tid < N) {  // window gather: cyclic shift + zero padding resolved once (swin_trans.py:207-225)
     const int win = z % nW, bi = z / nW;
     const int wy = win / nWx, wx = win - wy * nWx;
@@ -349,105 +380,124 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     tok[tid] = (oy < H && ox < W) ? (bi * H + oy) * W + ox : -1;
   }
   __syncthreads();
-  for (int i = tid; i < N * 3 * (HD / 8); i += 288) {
-    const int which = i / (N * (HD / 8));
-    const int rem = i - which * (N * (HD / 8));
-    const int row = rem / (HD / 8), d0 = (rem % (HD / 8)) * 8;
-    const int col = which * C + h * HD + d0;
-    const int tk = tok[row];
-    const uint4 v = tk >= 0 ? ldg16(qkv + (size_t)tk * 3 * C + col) : ldg16(qkv_bias + col);
-    T* dst = which == 0 ? Qs : (which == 1 ? Ks : Vs);
-    *reinterpret_cast<uint4*>(&dst[row * LD + d0]) = v;
-  }
-  __syncthreads();
-  uint32_t qa[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-    ldsm_x4(qa[ks], &Qs[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8]);
-  float s[18][4];
-#pragma unroll
-  for (int i = 0; i < 18; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-    for (int np = 0; np < 9; ++np) {
-      uint32_t kb[4];
-      const int mi = lane >> 3;
-      ldsm_x4(kb, &Ks[(np * 16 + (lane & 7) + (mi >> 1) * 8) * LD + ks * 16 + (mi & 1) * 8]);
-      mma16816<T>(s[2 * np], qa[ks], kb[0], kb[1]);
-      mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+  auto prefetch = [&](int h, int stage) {
+    T* dst0 = bufs + (size_t)stage * 3 * N * LD;
+    for (int i = tid; i < N * 3 * (HD / 8); i += 288) {
+      const int which = i / (N * (HD / 8));
+      const int rem = i - which * (N * (HD / 8));
+      const int row = rem / (HD / 8), d0 = (rem % (HD / 8)) * 8;
+      const int col = which * C + h * HD + d0;
+      const int tk = tok[row];
+      const T* src = tk >= 0 ? qkv + (size_t)tk * 3 * C + col : qkv_bias + col;
+      cp_async16(dst0 + (size_t)which * N * LD + row * LD + d0, src, 16);
     }
-  }
+    cp_async_commit();
+  };
+  prefetch(h0, 0);
   const float sc = rsqrtf((float)HD);
   const int r0 = warp * 16 + g, r1 = r0 + 8;
-  const float* rel0 = rel + ((size_t)h * N + r0) * N;
-  const float* rel1 = rel + ((size_t)h * N + r1) * N;
   const int reg0 = reg[r0], reg1 = reg[r1];
-  float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-  for (int nt = 0; nt < 18; ++nt) {
-    const int kj = nt * 8 + 2 * t4;
-    const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
-    const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
-    float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
-    if (shift > 0) {
-      const int ra = reg[kj], rb = reg[kj + 1];
-      m00 = ra != reg0 ? -100.f : 0.f; m01 = rb != reg0 ? -100.f : 0.f;
-      m10 = ra != reg1 ? -100.f : 0.f; m11 = rb != reg1 ? -100.f : 0.f;
+  const int tk0 = tok[r0], tk1 = tok[r1];
+#pragma unroll 1
+  for (int hi = 0; hi < HPC; ++hi) {
+    const int h = h0 + hi, stage = hi & 1;
+    if (hi + 1 < HPC) {
+      prefetch(h + 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    s[nt][0] = (s[nt][0] * sc + b0.x + m00) * kLog2e;
-    s[nt][1] = (s[nt][1] * sc + b0.y + m01) * kLog2e;
-    s[nt][2] = (s[nt][2] * sc + b1.x + m10) * kLog2e;
-    s[nt][3] = (s[nt][3] * sc + b1.y + m11) * kLog2e;
-    mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-    mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-  }
-  float sum[2] = {0.f, 0.f};
+    __syncthreads();
+    const T* Qs = bufs + (size_t)stage * 3 * N * LD;
+    const T* Ks = Qs + N * LD;
+    const T* Vs = Ks + N * LD;
+    uint32_t qa[2][4];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-  }
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4(qa[ks], &Qs[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8]);
+    float s[18][4];
 #pragma unroll
-  for (int nt = 0; nt < 18; ++nt) {
-    s[nt][0] = exp2f(s[nt][0] - mx[0]); s[nt][1] = exp2f(s[nt][1] - mx[0]);
-    s[nt][2] = exp2f(s[nt][2] - mx[1]); s[nt][3] = exp2f(s[nt][3] - mx[1]);
-    sum[0] += s[nt][0] + s[nt][1];
-    sum[1] += s[nt][2] + s[nt][3];
-  }
+    for (int i = 0; i < 18; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
-    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
-  }
-  float o[4][4];
+    for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < 9; ++kk) {
-    uint32_t pa[4];
-    pa[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-    for (int dp = 0; dp < 2; ++dp) {
-      uint32_t vb[4];
-      const int mi = lane >> 3;
-      ldsm_x4_t(vb, &Vs[(kk * 16 + (lane & 7) + (mi & 1) * 8) * LD + dp * 16 + (mi >> 1) * 8]);
-      mma16816<T>(o[2 * dp], pa, vb[0], vb[1]);
-      mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
+      for (int np = 0; np < 9; ++np) {
+        uint32_t kb[4];
+        const int mi = lane >> 3;
+        ldsm_x4(kb, &Ks[(np * 16 + (lane & 7) + (mi >> 1) * 8) * LD + ks * 16 + (mi & 1) * 8]);
+        mma16816<T>(s[2 * np], qa[ks], kb[0], kb[1]);
+        mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+      }
     }
-  }
+    const float* rel0 = rel + ((size_t)h * N + r0) * N;
+    const float* rel1 = rel + ((size_t)h * N + r1) * N;
+    float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int tk = tok[r ? r1 : r0];
-    if (tk < 0) continue;  // padded token: cropped (swin_trans.py:244-245)
-    const float inv = 1.f / sum[r];
+    for (int nt = 0; nt < 18; ++nt) {
+      const int kj = nt * 8 + 2 * t4;
+      const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
+      const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
+      float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
+      if (shift > 0) {
+        const int ra = reg[kj], rb = reg[kj + 1];
+        m00 = ra != reg0 ? -100.f : 0.f; m01 = rb != reg0 ? -100.f : 0.f;
+        m10 = ra != reg1 ? -100.f : 0.f; m11 = rb != reg1 ? -100.f : 0.f;
+      }
+      s[nt][0] = (fmaf(s[nt][0], sc, b0.x) + m00) * kLog2e;
+      s[nt][1] = (fmaf(s[nt][1], sc, b0.y) + m01) * kLog2e;
+      s[nt][2] = (fmaf(s[nt][2], sc, b1.x) + m10) * kLog2e;
+      s[nt][3] = (fmaf(s[nt][3], sc, b1.y) + m11) * kLog2e;
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float sum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<uint32_t*>(out + (size_t)tk * C + h * HD + i * 8 + 2 * t4) =
-          pack2<T>(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mx[0]); s[nt][1] = exp2f(s[nt][1] - mx[0]);
+      s[nt][2] = exp2f(s[nt][2] - mx[1]); s[nt][3] = exp2f(s[nt][3] - mx[1]);
+      sum[0] += s[nt][0] + s[nt][1];
+      sum[1] += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+    }
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {
+        uint32_t vb[4];
+        const int mi = lane >> 3;
+        ldsm_x4_t(vb, &Vs[(kk * 16 + (lane & 7) + (mi & 1) * 8) * LD + dp * 16 + (mi >> 1) * 8]);
+        mma16816<T>(o[2 * dp], pa, vb[0], vb[1]);
+        mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int tk = r ? tk1 : tk0;
+      if (tk < 0) continue;  // padded token: cropped (swin_trans.py:244-245)
+      const float inv = 1.f / sum[r];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint32_t*>(out + (size_t)tk * C + h * HD + i * 8 + 2 * t4) =
+            pack2<T>(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+    }
+    __syncthreads();   // this stage is refilled two iterations later
   }
 }
 
@@ -459,6 +509,8 @@ static int launch_flash(const Policy& pol, AttnDims dm, int hd, float* workspace
   dim3 grid(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
   PSALM_REQUIRE(dm.H <= 65535 && dm.B <= 65535, "%s: grid too large", what);
   PSALM_REQUIRE(dm.splits == 1 || workspace != nullptr, "%s: split-K needs a workspace", what);
+  PSALM_REQUIRE(((dm.Lk + 63) / 64 + dm.splits - 1) / dm.splits <= 128,
+                "%s: more than 128 key tiles per split (Lk=%d, splits=%d): raise splits", what, dm.Lk, dm.splits);
   static bool carveout_set = false;   // per (T, Policy) instantiation
   if (!carveout_set) {
     // 4 CTAs x 46 KB (HD = 64) per SM only fit if the L1/shared split favours shared memory; the driver's
@@ -505,26 +557,39 @@ int mma_cross_attention(const void* q, const void* k, const void* v, const uint3
   return launch_flash<T>(pol, dm, hd, workspace, st, "cross_attention(mma)");
 }
 
-int mma_window_attention(const void* qkv, const void* qkv_bias, const float* rel, void* out, int B, int H, int W,
-                         int C, int nh, int shift, int dtype, cudaStream_t st) {
+template <typename T>
+static int launch_window(const void* qkv, const void* qkv_bias, const float* rel, void* out, int B, int H, int W, int C,
+                         int nh, int shift, cudaStream_t st) {
   const int ws = 12;
   const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
   const int nWx = Wp / ws, nW = nWx * (Hp / ws);
-  dim3 grid(B * nW, nh);
-  PSALM_REQUIRE(nh <= 65535, "window_attention: too many heads");
-  static bool carveout_set = false;
-  if (!carveout_set) {  // two 35 KB CTAs per SM need more than the default shared-memory carve-out
-    cudaFuncSetAttribute(window_mma_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    cudaFuncSetAttribute(window_mma_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    carveout_set = true;
-  }
-  if (dtype == PSALM_BF16)
-    window_mma_kernel<__nv_bfloat16><<<grid, 288, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_bias, rel,
-                                                          (__nv_bfloat16*)out, H, W, Hp, Wp, shift, nh, C, nWx, nW);
-  else
-    window_mma_kernel<__half><<<grid, 288, 0, st>>>((const __half*)qkv, (const __half*)qkv_bias, rel, (__half*)out, H,
-                                                   W, Hp, Wp, shift, nh, C, nWx, nW);
+  constexpr size_t smem = sizeof(T) * 2 * 3 * 144 * 40 + sizeof(int) * 144 + 144;
+#define WIN(HPC)                                                                                                  \
+  do {                                                                                                            \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      cudaFuncSetAttribute(window_mma_kernel<T, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      cudaFuncSetAttribute(window_mma_kernel<T, HPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);       \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    dim3 grid(B * nW, nh / HPC);                                                                                  \
+    window_mma_kernel<T, HPC><<<grid, 288, smem, st>>>((const T*)qkv, (const T*)qkv_bias, rel, (T*)out, H, W, Hp,   \
+                                                      Wp, shift, nh, C, nWx, nW);                                 \
+  } while (0)
+  // enough CTAs for >= 2 waves of 148 SMs x 2 CTAs, otherwise prefer deeper per-CTA pipelining
+  const long long windows = (long long)B * nW;
+  if (nh % 4 == 0 && windows * (nh / 4) >= 600) WIN(4);
+  else if (nh % 2 == 0 && windows * (nh / 2) >= 148) WIN(2);
+  else WIN(1);
+#undef WIN
   return check_launch("window_mma_kernel");
+}
+
+int mma_window_attention(const void* qkv, const void* qkv_bias, const float* rel, void* out, int B, int H, int W,
+                         int C, int nh, int shift, int dtype, cudaStream_t st) {
+  PSALM_REQUIRE(nh <= 65535, "window_attention: too many heads");
+  if (dtype == PSALM_BF16) return launch_window<__nv_bfloat16>(qkv, qkv_bias, rel, out, B, H, W, C, nh, shift, st);
+  return launch_window<__half>(qkv, qkv_bias, rel, out, B, H, W, C, nh, shift, st);
 }
 
 }  // namespace psalm
