@@ -132,6 +132,9 @@ int psalm_cross_attention(const void* q, const void* k, const void* v, const uin
  * feats^T < 0) packed 32 keys / word + row_open; the logits are never written. */
 int psalm_mask_bits_fused(const void* mask_embed, const void* feats, uint32_t* bits, uint8_t* row_open, int B,
                           int Q, int P, int C, int dtype, void* stream);
+/* Implementation selector of psalm_mask_logits for 16-bit storage: 0 = auto (tcgen05 + TMEM kernel for
+ * P >= 8192, warp-level mma.sync below), 1 = mma.sync, 2 = tcgen05. */
+int psalm_set_mask_proj_impl(int impl);
 int psalm_mask_logits(const void* mask_embed, const void* feats, void* out, int B, int Q, int P, int C,
                       int dtype, int out_dtype, void* stream);
 int psalm_bilinear_tokens(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C, int dtype,

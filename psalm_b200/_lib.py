@@ -39,6 +39,7 @@ SIGNATURES = {
     "psalm_cross_attention_workspace_bytes": ([_c_i] * 5, ctypes.c_size_t),
     "psalm_cross_attention": ([_c_vp] * 7 + [_c_i] * 7 + [_c_vp], _c_i),
     "psalm_mask_bits_fused": ([_c_vp] * 4 + [_c_i] * 5 + [_c_vp], _c_i),
+    "psalm_set_mask_proj_impl": ([_c_i], _c_i),
     "psalm_mask_logits": ([_c_vp] * 3 + [_c_i] * 6 + [_c_vp], _c_i),
     "psalm_bilinear_tokens": ([_c_vp] * 2 + [_c_i] * 9 + [_c_vp], _c_i),
     "psalm_attn_mask_bits": ([_c_vp] * 3 + [_c_i] * 3 + [_c_vp], _c_i),

@@ -115,11 +115,19 @@ __global__ void attn_mask_bits_kernel(const T* __restrict__ logits, uint32_t* __
 }  // namespace psalm
 
 namespace psalm {
+int tc5_mask_proj(const void* me, const void* feats, void* out, int B, int Q, int P, int dtype, cudaStream_t st);
+static int g_mask_proj_impl = 0;   // 0 auto, 1 mma.sync, 2 tcgen05
 int mma_mask_proj(const void* me, const void* feats, void* out, uint32_t* bits, uint8_t* row_open, int B, int Q, int P,
                   int dtype, cudaStream_t st);
 }
 
 using namespace psalm;
+
+extern "C" int psalm_set_mask_proj_impl(int impl) {
+  PSALM_REQUIRE(impl >= 0 && impl <= 2, "set_mask_proj_impl: 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+  g_mask_proj_impl = impl;
+  return PSALM_OK;
+}
 
 extern "C" int psalm_mask_bits_fused(const void* mask_embed, const void* feats, uint32_t* bits, uint8_t* row_open,
                                      int B, int Q, int P, int C, int dtype, void* stream) {
@@ -135,6 +143,9 @@ extern "C" int psalm_mask_logits(const void* mask_embed, const void* feats, void
                                  int C, int dtype, int out_dtype, void* stream) {
   PSALM_REQUIRE(mask_embed && feats && out, "mask_logits: null pointer");
   PSALM_REQUIRE(out_dtype == dtype || out_dtype == PSALM_F32, "mask_logits: out dtype must be F32 or the input dtype");
+  if (dtype != PSALM_F32 && out_dtype == dtype && C == 256 && Q <= 128 &&
+      (g_mask_proj_impl == 2 || (g_mask_proj_impl == 0 && P >= 8192)))
+    return tc5_mask_proj(mask_embed, feats, out, B, Q, P, dtype, (cudaStream_t)stream);   // tcgen05 + TMEM
   if (dtype != PSALM_F32 && out_dtype == dtype && C == 256 && Q <= 112 && P % 2 == 0)
     return mma_mask_proj(mask_embed, feats, out, nullptr, nullptr, B, Q, P, dtype, (cudaStream_t)stream);
   dim3 grid((P + 127) / 128, (Q + 31) / 32, B);

@@ -152,3 +152,24 @@ def test_mask_bits_fused_and_mma_logits(dt, P, attn_impl):
     f2[0, :, 0] = -1.0          # row 5 of batch 0: every key blocked -> row_open
     _, ro2 = kernels.mask_bits(me2.cuda(), f2.cuda())
     assert int(ro2[0, 5]) == 1
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("B,Q,P", [(1, 100, 8192), (2, 100, 4096 + 96), (1, 128, 65536), (3, 7, 130)])
+def test_mask_projection_tcgen05(dt, B, Q, P, attn_impl):
+    """tcgen05 + TMEM mask projection (csrc/mask_proj_tc5.cu) vs the fp32 restatement; also vs the mma.sync
+    kernel (bit-for-bit is not required: both accumulate in fp32 but in different orders)."""
+    if attn_impl == "simt":
+        pytest.skip("independent of the attention implementation switch")
+    from psalm_b200 import _lib
+    torch.manual_seed(P + Q)
+    me = torch.randn(B, Q, 256).to(DT[dt])
+    f = torch.randn(B, P, 256).to(DT[dt])
+    ref = emu.mask_logits(me.float(), f.float(), torch.float32)
+    try:
+        _lib.check(_lib.lib().psalm_set_mask_proj_impl(2), "set_mask_proj_impl")
+        out = kernels.mask_logits(me.cuda(), f.cuda())
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().psalm_set_mask_proj_impl(0)
+    _close(out, ref, dt)
