@@ -294,13 +294,15 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
   const float rx = ((float)qx + 0.5f) / (float)lv.W[ql];
   const float ry = ((float)qy + 0.5f) / (float)lv.H[ql];
 
-  // ---- parameters of the samples this lane owns
-  uint32_t pidx[SPL];
+  // ---- parameters of the samples this lane owns: four corner offsets (elements, relative to this
+  //      head's value plane; 32-bit) and the four bilinear x attention weights
+  constexpr int DC = G * CH;   // == D (checked on the host), compile-time for the address arithmetic
+  uint32_t poff[SPL][4];
   float pw[SPL][4];
 #pragma unroll
   for (int j = 0; j < SPL; ++j) {
     const int s = cl + j * G;
-    pidx[j] = 0;
+    poff[j][0] = poff[j][1] = poff[j][2] = poff[j][3] = 0u;
     pw[j][0] = pw[j][1] = pw[j][2] = pw[j][3] = 0.f;
     if (s < LP) {
       const int l = s / PT;
@@ -328,33 +330,36 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
         pw[j][3] = (vy1 && vx1) ? ly * lx * aw : 0.f;
         const int y0c = y0 < 0 ? 0 : y0, x0c = x0 < 0 ? 0 : x0;
         const int y1c = y0 + 1 > H - 1 ? H - 1 : y0 + 1, x1c = x0 + 1 > W - 1 ? W - 1 : x0 + 1;
-        pidx[j] = (uint32_t)(y0c * W + x0c) | ((uint32_t)(x1c - x0c) << 30) | ((uint32_t)(y1c - y0c) << 31);
+        const int st = lv.start[l];
+        poff[j][0] = (uint32_t)((st + y0c * W + x0c) * DC);
+        poff[j][1] = (uint32_t)((st + y0c * W + x1c) * DC);
+        poff[j][2] = (uint32_t)((st + y1c * W + x0c) * DC);
+        poff[j][3] = (uint32_t)((st + y1c * W + x1c) * DC);
       }
     }
   }
 
-  const TV* __restrict__ vb = value + ((size_t)b * M + m) * (size_t)S * D + cl * CH;
+  const TV* __restrict__ vb = value + ((size_t)b * M + m) * (size_t)S * DC + cl * CH;
   float acc[CH];
 #pragma unroll
   for (int i = 0; i < CH; ++i) acc[i] = 0.f;
 
 #pragma unroll
   for (int s = 0; s < LP; ++s) {
-    const int l = s / PT, owner = gbase + (s % G), j = s / G;
-    const uint32_t pk = __shfl_sync(0xffffffffu, pidx[j], owner);
+    const int owner = gbase + (s % G), j = s / G;
+    const uint32_t o00 = __shfl_sync(0xffffffffu, poff[j][0], owner);
+    const uint32_t o01 = __shfl_sync(0xffffffffu, poff[j][1], owner);
+    const uint32_t o10 = __shfl_sync(0xffffffffu, poff[j][2], owner);
+    const uint32_t o11 = __shfl_sync(0xffffffffu, poff[j][3], owner);
     const float w00 = __shfl_sync(0xffffffffu, pw[j][0], owner);
     const float w01 = __shfl_sync(0xffffffffu, pw[j][1], owner);
     const float w10 = __shfl_sync(0xffffffffu, pw[j][2], owner);
     const float w11 = __shfl_sync(0xffffffffu, pw[j][3], owner);
-    const int W = lv.W[l];
-    const TV* p00 = vb + ((size_t)lv.start[l] + (pk & 0x3fffffffu)) * D;
-    const TV* p01 = p00 + ((pk >> 30) & 1u) * D;
-    const size_t dyo = (size_t)(pk >> 31) * W * D;
     float f00[CH], f01[CH], f10[CH], f11[CH];
-    load16_as_f32<TV>(p00, f00);
-    load16_as_f32<TV>(p01, f01);
-    load16_as_f32<TV>(p00 + dyo, f10);
-    load16_as_f32<TV>(p01 + dyo, f11);
+    load16_as_f32<TV>(vb + o00, f00);
+    load16_as_f32<TV>(vb + o01, f01);
+    load16_as_f32<TV>(vb + o10, f10);
+    load16_as_f32<TV>(vb + o11, f11);
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       acc[i] = fmaf(w00, f00[i], acc[i]);
@@ -363,7 +368,7 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
       acc[i] = fmaf(w11, f11[i], acc[i]);
     }
   }
-  if (active) store16_from_f32<TV>(out + (((size_t)b * S + q) * M + m) * (size_t)D + cl * CH, acc);
+  if (active) store16_from_f32<TV>(out + (((size_t)b * S + q) * M + m) * (size_t)DC + cl * CH, acc);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -467,6 +472,7 @@ static int launch_fused(const void* value, const void* ow, void* out, const int6
   PSALM_REQUIRE(D % CH == 0, "msda_fused: D=%d not a multiple of %d", D, CH);
   const int G = D / CH;
   PSALM_REQUIRE(G == 4 || G == 8, "msda_fused: D=%d unsupported (need D/%d in {4,8})", D, CH);
+  PSALM_REQUIRE((long long)S * D < (1ll << 31), "msda_fused: S*D=%lld exceeds the 32-bit corner offsets", (long long)S * D);
   PSALM_REQUIRE((L == 3 || L == 4) && P == 4, "msda_fused: (L,P)=(%d,%d) unsupported", L, P);
   MsdaLevels lv;
   int tiles = 0;

@@ -7,19 +7,23 @@ from . import _lib
 from .msda import ms_deform_attn_forward, msda_encoder_fused  # noqa: F401  (re-exported)
 
 _LAUNCHES = [0]  # kernels launched through this module (bench.py's gpu_launches counter)
-PROFILE_EVENTS = None  # bench.py sets this to a list: (start, end) CUDA events around each MSDeformAttn launch
+PROFILE_EVENTS = None  # bench.py sets this to a dict: name -> [(start, end) CUDA events] around hot-kernel launches
+
+
+def timed(name, fn, *args, **kw):
+    """Run a hot-kernel launch; when bench.py profiles, bracket it with CUDA events on the current stream."""
+    if PROFILE_EVENTS is None:
+        return fn(*args, **kw)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn(*args, **kw)
+    b.record()
+    PROFILE_EVENTS.setdefault(name, []).append((a, b))
+    return out
 
 
 def timed_msda(fn, *args):
-    """Run an MSDeformAttn launch; when bench.py profiles, bracket it with CUDA events on the current stream."""
-    if PROFILE_EVENTS is None:
-        return fn(*args)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    out = fn(*args)
-    b.record()
-    PROFILE_EVENTS.append((a, b))
-    return out
+    return timed("msda", fn, *args)
 
 
 def launches():

@@ -112,7 +112,7 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             q = F.linear(output + qpos, w["x%d.q.w" % i], w["x%d.q.b" % i])
             k = F.linear(kins[li], w["x%d.k.w" % i], w["x%d.k.b" % i])
             v = F.linear(srcs[li], w["x%d.v.w" % i], w["x%d.v.b" % i])
-            a = kernels.cross_attention(q, k, v, bits, row_open, nh)
+            a = kernels.timed("masked_cross_attention_%d" % k.shape[1], kernels.cross_attention, q, k, v, bits, row_open, nh)
             output = kernels.add_layer_norm(output, w["x%d.n.w" % i], w["x%d.n.b" % i],
                                             r1=F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]))
             # query self-attention (:35-45): q = k = tgt + query_pos, v = tgt
@@ -135,7 +135,7 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
         if class_name_embedding is not None:
             out["pred_class_name_logits"] = torch.bmm(self._mlp("CLASS_proj", 2, dec),
                                                       class_name_embedding.to(self.dtype).transpose(1, 2))
-        out["pred_masks"] = kernels.mask_logits(me.contiguous(), mask_features)
+        out["pred_masks"] = kernels.timed("mask_projection", kernels.mask_logits, me.contiguous(), mask_features)
         if return_trace:
             out["trace_pooled_logits"] = trace
         return out

@@ -64,7 +64,7 @@ class PhiModel:
                 h, x = kernels.add_layer_norm(h, w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps, r1=a, r2=f, return_sum=True)
             qkv = F.linear(x, w["%d.qkv.w" % i], w["%d.qkv.b" % i]).view(B, T, 3, nh, hd)
             kernels.rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd)
-            a = kernels.causal_attention(qkv, kv, B, T, nh, hd)
+            a = kernels.timed("causal_attention", kernels.causal_attention, qkv, kv, B, T, nh, hd)
             a = F.linear(a, w["%d.dense.w" % i], w["%d.dense.b" % i])
             f = self._fc1_gelu(x, i)
             f = F.linear(f, w["%d.fc2.w" % i], w["%d.fc2.b" % i])

@@ -83,7 +83,8 @@ class SwinTransformer:
                 else:
                     x, h = LN(x, w[p + "norm1.w"], w[p + "norm1.b"], r1=delta, return_sum=True)
                 qkv = F.linear(h, w[p + "attn.qkv.w"], w[p + "attn.qkv.b"])
-                a = kernels.window_attention(qkv, w[p + "attn.qkv.b"], w[p + "rel"], B, Wh, Ww, C, nh, ws, shift)
+                a = kernels.timed("window_attention_stage%d" % s, kernels.window_attention, qkv, w[p + "attn.qkv.b"],
+                                  w[p + "rel"], B, Wh, Ww, C, nh, ws, shift)
                 a = F.linear(a, w[p + "attn.proj.w"], w[p + "attn.proj.b"])
                 x, h = LN(x, w[p + "norm2.w"], w[p + "norm2.b"], r1=a, return_sum=True)
                 h = F.gelu(F.linear(h, w[p + "mlp.fc1.w"], w[p + "mlp.fc1.b"]))
