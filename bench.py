@@ -197,6 +197,10 @@ def run_ours(args, rank, world, local_rank):
     # roofline leg: the same K steps launched eagerly (a CUDA graph cannot carry timing events), with
     # CUDA events on the launch stream around every MSDeformAttn launch; also counts our launches per step
     def step_eager():
+        # eager launches are CPU bound (~30 ms of Python per image vs ~10 ms of GPU work): park the GPU on a
+        # ~40 ms spin first so that every kernel of the step is already queued when it runs and the event
+        # pairs below measure device time, not launch gaps
+        torch.cuda._sleep(80_000_000)
         out = model.forward_core(images_d, plan_d)
         return model.post_process(out, (IMG, IMG), inp["seg_info"])
     step_eager()
