@@ -132,11 +132,12 @@ class PSALM:
         return out
 
     # ---- CUDA-graph replay of the device-only part -------------------------------------------------
-    def forward_core_graphed(self, images, plan):
+    def forward_core_graphed(self, images, plan, lane=0):
         """Same results as forward_core, replayed from a CUDA graph captured per (image size, prompt
-        structure): the ~2000 launches of one image become one graph launch (the reference issues them
-        one by one from Python, plus ~150 extra tiny launches in its decoder)."""
-        key = (tuple(images.shape), plan.B, plan.T, plan.n_img, plan.any_padding,
+        structure): the ~800 launches of one image become one graph launch (the reference issues them
+        one by one from Python, plus ~150 extra tiny launches in its decoder).  `lane` selects an
+        independent graph + static buffers so that several images can be in flight on different streams."""
+        key = (lane, tuple(images.shape), plan.B, plan.T, plan.n_img, plan.any_padding,
                None if plan.cls_pool is None else tuple(plan.cls_pool.shape), plan.refer_pool is not None,
                None if plan.pad_pos is None else int(plan.pad_pos.numel()))
         if not hasattr(self, "_graphs"):
