@@ -254,3 +254,15 @@ def mask_bits(mask_embed, feats):
     _lib.check(rc, "psalm_mask_bits_fused")
     _count(2)
     return bits, row_open
+
+
+def linear_act(x, weight, bias, act):
+    """Linear + activation with the activation in the library GEMM's epilogue (cuBLASLt) for 16-bit CUDA
+    tensors: act = "relu" or "gelu_tanh" (gelu_new).  Library plumbing, not a custom kernel."""
+    import torch.nn.functional as F
+    if x.is_cuda and x.dtype != torch.float32:
+        shp = x.shape
+        y = torch._addmm_activation(bias, x.reshape(-1, shp[-1]), weight.t(), use_gelu=(act == "gelu_tanh"))
+        return y.view(*shp[:-1], weight.shape[0])
+    y = F.linear(x, weight, bias)
+    return F.relu(y) if act == "relu" else F.gelu(y, approximate="tanh")

@@ -54,9 +54,10 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
 
     def _mlp(self, name, n, x):
         for j in range(n):
-            x = F.linear(x, self.w["%s.%d.w" % (name, j)], self.w["%s.%d.b" % (name, j)])
             if j < n - 1:
-                x = F.relu(x)
+                x = kernels.linear_act(x, self.w["%s.%d.w" % (name, j)], self.w["%s.%d.b" % (name, j)], "relu")
+            else:
+                x = F.linear(x, self.w["%s.%d.w" % (name, j)], self.w["%s.%d.b" % (name, j)])
         return x
 
     def _heads_common(self, output):
@@ -122,7 +123,7 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             output = kernels.add_layer_norm(output, w["s%d.n.w" % i], w["s%d.n.b" % i],
                                             r1=F.linear(a, w["s%d.o.w" % i], w["s%d.o.b" % i]))
             # FFN (:158-162)
-            f = F.linear(F.relu(F.linear(output, w["f%d.linear1.w" % i], w["f%d.linear1.b" % i])),
+            f = F.linear(kernels.linear_act(output, w["f%d.linear1.w" % i], w["f%d.linear1.b" % i], "relu"),
                          w["f%d.linear2.w" % i], w["f%d.linear2.b" % i])
             output = kernels.add_layer_norm(output, w["f%d.norm.w" % i], w["f%d.norm.b" % i], r1=f)
             if i < cfg.dec_layers - 1:

@@ -72,9 +72,4 @@ class PhiModel:
 
     def _fc1_gelu(self, x, i):
         """fc1 + gelu_new: bias and tanh-GELU run in the library GEMM's epilogue (cuBLASLt) on the GPU."""
-        w = self.w
-        if x.is_cuda and x.dtype != torch.float32:
-            B, T, C = x.shape
-            y = torch._addmm_activation(w["%d.fc1.b" % i], x.view(B * T, C), w["%d.fc1.w" % i].t(), use_gelu=True)
-            return y.view(B, T, -1)
-        return F.gelu(F.linear(x, w["%d.fc1.w" % i], w["%d.fc1.b" % i]), approximate="tanh")
+        return kernels.linear_act(x, self.w["%d.fc1.w" % i], self.w["%d.fc1.b" % i], "gelu_tanh")

@@ -126,7 +126,7 @@ class MSDeformAttnPixelDecoder:
             kernels._count()
             src = kernels.add_layer_norm(src, w["e%d.norm1.w" % i], w["e%d.norm1.b" % i],
                                          r1=F.linear(a, w["e%d.op.w" % i], w["e%d.op.b" % i]))
-            f = F.linear(F.relu(F.linear(src, w["e%d.linear1.w" % i], w["e%d.linear1.b" % i])),
+            f = F.linear(kernels.linear_act(src, w["e%d.linear1.w" % i], w["e%d.linear1.b" % i], "relu"),
                          w["e%d.linear2.w" % i], w["e%d.linear2.b" % i])
             src = kernels.add_layer_norm(src, w["e%d.norm2.w" % i], w["e%d.norm2.b" % i], r1=f)
         outs = [t.contiguous() for t in torch.split(src, [h_ * w_ for h_, w_ in shapes], dim=1)]
