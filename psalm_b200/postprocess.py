@@ -131,17 +131,27 @@ def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8, 
     return pan.view(H, W).to(torch.int32), info
 
 
-def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_list=None, semantic_on=False,
-                      instance_on=False, panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8, ovl_thr=0.8):
-    """All task heads of one image from the LOW-RESOLUTION mask logits [Q,H4,W4] with one fused kernel
-    (csrc/postproc.cu) — same results as the functions above applied to the up-sampled [Q,H,W] map, which
-    is never materialised.  Small [Q, n_cls] tensor algebra stays in torch; ONE D2H copy carries what the
-    host-side panoptic merge and the instance count need."""
+_THING_CACHE = {}
+
+
+def thing_tensor(is_thing_list, device):
+    """Boolean `is_thing` lookup table on the device, cached by content (built once per class vocabulary)."""
+    key = (tuple(bool(t) for t in is_thing_list), str(device))
+    if key not in _THING_CACHE:
+        _THING_CACHE[key] = torch.tensor(key[0], dtype=torch.bool, device=device)
+    return _THING_CACHE[key]
+
+
+def fused_device(kernels, logits, H, W, cls=None, SEG_cls=None, thing=None, semantic_on=False, instance_on=False,
+                 panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8):
+    """Device part of the fused task heads (no host synchronisation, CUDA-graph capturable): small
+    [Q, n_cls] tensor algebra in torch + ONE fused kernel (csrc/postproc.cu) on the LOW-RESOLUTION mask
+    logits [Q,H4,W4].  Returns device tensors plus `hostvec`, the one vector the host part needs."""
     Q = logits.shape[0]
     dev = logits.device
     probsT = wq = negq = slots = None
     ncls = 0
-    r = {}
+    d = dict(Q=Q, H=H, W=W)
     if cls is not None:
         probs_full = F.softmax(cls.float(), dim=-1)
         probs = probs_full[:, :-1]
@@ -154,11 +164,11 @@ def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_li
         keep = labels.ne(ncls) & (scores > obj_thr)
         wq = torch.where(keep, scores, torch.zeros_like(scores)).contiguous()
         negq = (keep.float() - 1.0).contiguous()
+    s = lab = qi = keep_i = None
     if instance_on:
         s, idx = probs.flatten(0, 1).topk(topk, sorted=False)
         lab, qi = idx % ncls, idx // ncls
         if panoptic_on:
-            thing = torch.as_tensor([bool(t) for t in is_thing_list], device=dev)
             keep_i = thing[lab]
             order = torch.sort((~keep_i).to(torch.uint8), stable=True).indices      # kept slots first
             s, lab, qi, keep_i = s[order], lab[order], qi[order], keep_i[order]
@@ -168,33 +178,43 @@ def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_li
     elif referring_on:
         s, qi = torch.sigmoid(SEG_cls.float()).flatten(0, 1).topk(topk, sorted=False)
         keep_i = torch.ones_like(qi, dtype=torch.bool)
-        lab = None
         slots = qi.to(torch.int32).contiguous()
     k = kernels.postproc_fused(logits.contiguous(), H, W, probsT, wq, negq, slots, ncls)
     st = k["stats"]
-    if semantic_on:
-        r["sem_seg"] = k["sem_seg"]
-    n_inst = None
-    host_rows = []
+    d.update(sem_seg=k["sem_seg"], inst_masks=k["inst_masks"], ids=k["ids"], in_mask=k["in_mask"], lab=lab, qi=qi)
+    rows = []
     if slots is not None:
-        host_rows.append(keep_i.sum().view(1).float())
+        rows.append(keep_i.sum().view(1).float())
+        d["inst_scores"] = s * (st[:, 1] / (st[:, 0] + 1e-6))[qi]               # class score x per-query mask score
     if panoptic_on:
-        host_rows += [keep.float(), labels.float(), st[:, 3], st[:, 2], st[:, 4]]
-    host = torch.cat(host_rows).cpu().numpy() if host_rows else None        # the one D2H copy
+        rows += [keep.float(), labels.float(), st[:, 3], st[:, 2], st[:, 4]]
+    d["hostvec"] = torch.cat(rows) if rows else None
+    d["has_inst"], d["has_pan"], d["has_sem"] = slots is not None, bool(panoptic_on), bool(semantic_on)
+    return d
+
+
+def fused_host(d, is_thing_list=None, ovl_thr=0.8):
+    """Host part: the ONE D2H copy, the sequential panoptic merge rule on <= Q integers
+    (llava_phi.py:355-384) and the final id lookup."""
+    Q, H, W = d["Q"], d["H"], d["W"]
+    r = {}
+    if d["has_sem"]:
+        r["sem_seg"] = d["sem_seg"]
+    host = d["hostvec"].cpu().numpy() if d["hostvec"] is not None else None        # the one D2H copy
     pos = 0
-    if slots is not None:
+    if d["has_inst"]:
         n_inst = int(host[0])
         pos = 1
-        ms = st[:, 1] / (st[:, 0] + 1e-6)                                   # per-query mask score
         inst = Instances((H, W))
-        inst.pred_masks = k["inst_masks"][:n_inst]
+        inst.pred_masks = d["inst_masks"][:n_inst]
         inst.pred_boxes = Boxes(torch.zeros(n_inst, 4))
-        inst.scores = (s * ms[qi])[:n_inst]
-        if lab is not None:
-            inst.pred_classes = lab[:n_inst]
-        inst.query_index = qi[:n_inst]
+        inst.scores = d["inst_scores"][:n_inst]
+        if d["lab"] is not None:
+            inst.pred_classes = d["lab"][:n_inst]
+        inst.query_index = d["qi"][:n_inst]
         r["instances"] = inst
-    if panoptic_on:
+    if d["has_pan"]:
+        dev = d["ids"].device
         hk = host[pos:].reshape(5, Q)
         seg_of_query = np.zeros(Q, np.int32)
         info, stuff, cur = [], {}, 0
@@ -218,6 +238,16 @@ def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_li
             pan = torch.zeros((H, W), dtype=torch.int32, device=dev)
         else:
             lut = torch.from_numpy(seg_of_query).to(dev)
-            pan = torch.where(k["in_mask"].bool(), lut[k["ids"].long()], torch.zeros((), dtype=torch.int32, device=dev))
+            pan = torch.where(d["in_mask"].bool(), lut[d["ids"].long()], torch.zeros((), dtype=torch.int32, device=dev))
         r["panoptic_seg"] = (pan.to(torch.int32), info)
     return r
+
+
+def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_list=None, semantic_on=False,
+                      instance_on=False, panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8, ovl_thr=0.8):
+    """All task heads of one image from the LOW-RESOLUTION mask logits with one fused kernel — same results
+    as the step-by-step functions above applied to the up-sampled [Q,H,W] map, which is never materialised."""
+    thing = thing_tensor(is_thing_list, logits.device) if (panoptic_on and instance_on) else None
+    d = fused_device(kernels, logits, H, W, cls, SEG_cls, thing, semantic_on, instance_on, panoptic_on, referring_on,
+                     topk, obj_thr)
+    return fused_host(d, is_thing_list, ovl_thr)

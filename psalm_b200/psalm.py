@@ -10,6 +10,10 @@ Keeps the operator surface of `PSALM(PhiForCausalLM, LlavaMetaForCausalLM)` that
     model.predictor(x, mask_features, None, seg_query, SEG_embedding, class_name_embedding, None)
 and loads the reference checkpoint layout unchanged (layout.py / loader.py).
 
+With `use_cuda_graph=True` the network and the device part of the task heads replay from one CUDA graph;
+the returned tensors then alias the graph's static buffers and are valid until the next `eval_seg` call on
+the same model (consume or clone them first, as the reference's eval loops do with `evaluator.process`).
+
 How it differs from the reference on purpose (results are unchanged):
   * Swin runs ONCE per image (the reference runs it twice on identical input, llava_phi.py:449 and :223);
   * every image of the batch is post-processed (the reference returns inside the loop, llava_phi.py:1472);
@@ -132,12 +136,32 @@ class PSALM:
         return out
 
     # ---- CUDA-graph replay of the device-only part -------------------------------------------------
+    def _post_device(self, out, image_hw):
+        """Device part of the fused post-processing for every image (capturable); None if not applicable."""
+        Hi, Wi = image_hw
+        d = self.size_divisibility
+        Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d
+        H4, W4 = out["mask_size"]
+        B, Q = out["pred_masks"].shape[:2]
+        cls = out["pred_class_name_logits"]
+        if not (self.fused_postprocess and Hp >= 2 * H4 and Wp >= 2 * W4 and Q <= 104 and
+                (cls is None or cls.shape[-1] - 1 <= 144)):
+            return None
+        from . import kernels
+        thing = PP.thing_tensor(self.is_thing_list, self.device) if (self.panoptic_on and self.instance_on) else None
+        pm = out["pred_masks"].view(B, Q, H4, W4)
+        return [PP.fused_device(kernels, pm[b], Hp, Wp, cls[b] if cls is not None else None,
+                                out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None, thing,
+                                self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
+                                self.test_topk_per_image, self.cfg.mask.object_mask_threshold) for b in range(B)]
+
     def forward_core_graphed(self, images, plan, lane=0):
         """Same results as forward_core, replayed from a CUDA graph captured per (image size, prompt
         structure): the ~800 launches of one image become one graph launch (the reference issues them
         one by one from Python, plus ~150 extra tiny launches in its decoder).  `lane` selects an
         independent graph + static buffers so that several images can be in flight on different streams."""
-        key = (lane, tuple(images.shape), plan.B, plan.T, plan.n_img, plan.any_padding,
+        key = (lane, self.seg_task, tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), plan.B,
+               plan.T, plan.n_img, plan.any_padding,
                None if plan.cls_pool is None else tuple(plan.cls_pool.shape), plan.refer_pool is not None,
                None if plan.pad_pos is None else int(plan.pad_pos.numel()))
         if not hasattr(self, "_graphs"):
@@ -153,14 +177,17 @@ class PSALM:
                 setattr(static_plan, n, None if t is None else t.clone())
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
+            hw = tuple(images.shape[-2:])
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self.forward_core(static_img, static_plan)
+                    o = self.forward_core(static_img, static_plan)
+                    o["post"] = self._post_device(o, hw)
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 static_out = self.forward_core(static_img, static_plan)
+                static_out["post"] = self._post_device(static_out, hw)   # task heads' device part, same graph
             ent = (g, static_img, static_plan, static_out)
             self._graphs[key] = ent
         g, static_img, static_plan, static_out = ent
@@ -240,6 +267,10 @@ class PSALM:
             cls_b = out["pred_class_name_logits"][b] if out["pred_class_name_logits"] is not None else None
             seg_b = out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None
             trivial = (oh, ow) == (Hp, Wp) and (height, width) == (Hp, Wp)
+            if trivial and out.get("post") is not None:
+                results.append(PP.fused_host(out["post"][b], getattr(self, "is_thing_list", None),
+                                             self.cfg.mask.overlap_threshold))
+                continue
             if self.fused_postprocess and trivial and Hp >= 2 * H4 and Wp >= 2 * W4 and Q <= 104 and \
                     (cls_b is None or cls_b.shape[-1] - 1 <= 144):
                 from . import kernels

@@ -104,3 +104,24 @@ def test_full_size_bf16_smoke():
     assert torch.equal(pan, r2[0]["panoptic_seg"][0]) and torch.equal(sem, r2[0]["sem_seg"])
     inst = r1[0]["instances"]
     assert inst.pred_masks.shape[1:] == (1024, 1024) and torch.isfinite(inst.scores).all()
+
+
+def test_cuda_graph_replay_matches_eager():
+    """PSALM(use_cuda_graph=True): the captured graph (network + fused task heads) gives the same results as
+    eager launches, also when replayed for a second image with the same prompt structure."""
+    from psalm_b200.psalm import PSALM
+    task, H, W, ncls, seed, batch, ragged = ("panoptic", 192, 192, 20, 0, 1, False)
+    sd = synth.synth_state_dict(SMALL, seed=seed)
+    eager = PSALM(sd, SMALL, torch.bfloat16, "cuda", task, use_cuda_graph=False)
+    graphed = PSALM(sd, SMALL, torch.bfloat16, "cuda", task, use_cuda_graph=True)
+    for s2 in (1, 2, 1):
+        inp = synth.synth_inputs(batch=batch, height=H, width=W, task=task, n_classes=ncls, seed=s2)
+        kw = {k: inp[k] for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "is_thing_list")}
+        a = eager.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                           seg_info=inp["seg_info"], **kw)
+        b = graphed.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                             seg_info=inp["seg_info"], **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(a[0]["panoptic_seg"][0], b[0]["panoptic_seg"][0]) and a[0]["panoptic_seg"][1] == b[0]["panoptic_seg"][1]
+        assert torch.equal(a[0]["sem_seg"], b[0]["sem_seg"])
+        assert torch.allclose(a[0]["instances"].scores, b[0]["instances"].scores, rtol=1e-5, atol=1e-7)
