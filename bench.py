@@ -308,7 +308,13 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "msda_encoder_fused_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
-                         "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B = 1 from the committed
+                         # `ncu --set full` capture (profiles/r1i_msda_fused_bf16_ncu_details.txt): 23.43 MB read +
+                         # 0.01 MB written inside the capture window (the 11 MB output stays in the 126 MB L2)
+                         "traffic": 23439104 * B if args.dtype != "f32" else None,
+                         "traffic_source": "ncu capture committed under profiles/ (not measured in this run)",
+                         "peak_source": peak_src,
                          "avg_us": avg_us, "launches_timed": len(msda_us), "algorithmic_bytes_per_launch": alg,
                          "timed_in": "K eager steps of the same workload, CUDA events on the launch stream"},
             "roofline_extra": [dict(e, frac=e["achieved_gbs"] / hbm, bound="hbm", peak=hbm) for e in extra]}
