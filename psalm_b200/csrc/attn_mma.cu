@@ -126,13 +126,19 @@ struct CrossMma {
 // ------------------------------------------------------------------------------------------------
 // flash kernel: grid = (q_tiles * splits, H, B), block = 128 (4 warps x 16 query rows)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int HD, typename Policy>
-__global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm, float* __restrict__ part) {
+// KG = key groups: the CTA has 4*KG warps; warp group `kg` walks the key tiles kt0+kg, kt0+kg+KG, ... with its
+// own double-buffered K/V stages and named barrier, and the groups' (m, l, O) partials are merged through
+// shared memory at the end (intra-CTA split-K).  At T ~ 900 / 100 queries the kernel is bound by the
+// per-warp instruction latency of the longest CTA, so halving that CTA's tile count is what pays.
+template <typename T, int HD, typename Policy, int KG>
+__global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Policy pol, AttnDims dm, float* __restrict__ part) {
   constexpr int BQ = 64, BK = 64, LD = HD + 8;
-  __shared__ __align__(16) T Qs[BQ * LD];
-  __shared__ __align__(16) T KVs[2][2][BK * LD];   // [stage][K|V]
-  __shared__ unsigned long long kvbits[128];       // per key tile: keys beyond Lk / padded keys (bit = blocked)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  extern __shared__ __align__(16) unsigned char flash_smem[];
+  T* Qs = reinterpret_cast<T*>(flash_smem);                                   // [BQ * LD]
+  T* KVbase = Qs + BQ * LD;                                                   // [KG][2 stages][K|V][BK * LD]
+  unsigned long long* kvbits = reinterpret_cast<unsigned long long*>(KVbase + KG * 4 * BK * LD);   // [128]
+  const int kg = threadIdx.x >> 7;                 // key group of this warp
+  const int tid = threadIdx.x & 127, warp = tid >> 5, lane = tid & 31;   // indices inside the group
   const int g = lane >> 2, t4 = lane & 3;
   // heavy (late, causal) query tiles first: better tail balance
   const int nqt = (dm.Lq + BQ - 1) / BQ;
@@ -148,11 +154,19 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
     kt1 = e < kt1 ? e : kt1;
   }
   // ---- Q tile -> smem -> A fragments in registers
-  for (int i = tid; i < BQ * HD / 8; i += 128) {
+  for (int i = threadIdx.x; i < BQ * HD / 8; i += 128 * KG) {
     const int row = i / (HD / 8), d0 = (i % (HD / 8)) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (q0 + row < dm.Lq) v = pol.load8(0, b, h, q0 + row, d0);
     *reinterpret_cast<uint4*>(&Qs[row * LD + d0]) = v;
+  }
+  for (int t = kt0 + (int)threadIdx.x; t < kt1; t += 128 * KG) {
+    unsigned long long m = 0ull;
+    for (int j = 0; j < BK; ++j) {
+      const int kj = t * BK + j;
+      if (kj >= dm.Lk || pol.key_invalid(b, kj)) m |= 1ull << j;
+    }
+    kvbits[t - kt0] = m;
   }
   __syncthreads();
   uint32_t qa[HD / 16][4];
@@ -167,37 +181,36 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
   const float sc = dm.scale * kLog2e;   // scores are tracked in the log2 domain
 
+  T* KVg = KVbase + (size_t)kg * 4 * BK * LD;    // this group's [2 stages][K|V] tiles
+  auto group_sync = [&]() {
+    if constexpr (KG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, 128;\n" ::"r"(1 + kg) : "memory");
+  };
   auto prefetch = [&](int kt, int stage) {
     for (int i = tid; i < BK * HD / 8; i += 128) {
       const int row = i / (HD / 8), d0 = (i % (HD / 8)) * 8;
       const int kj = kt * BK + row;
       const bool ok = kj < dm.Lk;
       const int kc = ok ? kj : 0;
-      cp_async16(&KVs[stage][0][row * LD + d0], pol.ptr(1, b, h, kc, d0), ok ? 16 : 0);
-      cp_async16(&KVs[stage][1][row * LD + d0], pol.ptr(2, b, h, kc, d0), ok ? 16 : 0);
+      cp_async16(&KVg[(stage * 2 + 0) * BK * LD + row * LD + d0], pol.ptr(1, b, h, kc, d0), ok ? 16 : 0);
+      cp_async16(&KVg[(stage * 2 + 1) * BK * LD + row * LD + d0], pol.ptr(2, b, h, kc, d0), ok ? 16 : 0);
     }
     cp_async_commit();
   };
-  for (int t = kt0 + tid; t < kt1; t += 128) {
-    unsigned long long m = 0ull;
-    for (int j = 0; j < BK; ++j) {
-      const int kj = t * BK + j;
-      if (kj >= dm.Lk || pol.key_invalid(b, kj)) m |= 1ull << j;
-    }
-    kvbits[t - kt0] = m;
-  }
-  if (kt0 < kt1) prefetch(kt0, 0);
-  for (int kt = kt0; kt < kt1; ++kt) {
-    const int stage = (kt - kt0) & 1;
-    if (kt + 1 < kt1) {
-      prefetch(kt + 1, stage ^ 1);
+  const int ktg0 = kt0 + kg;
+  if (ktg0 < kt1) prefetch(ktg0, 0);
+  int itn = 0;
+  for (int kt = ktg0; kt < kt1; kt += KG, ++itn) {
+    const int stage = itn & 1;
+    if (kt + KG < kt1) {
+      prefetch(kt + KG, stage ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
-    const T* Ks = KVs[stage][0];
-    const T* Vs = KVs[stage][1];
+    group_sync();
+    const T* Ks = KVg + (stage * 2 + 0) * BK * LD;
+    const T* Vs = KVg + (stage * 2 + 1) * BK * LD;
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -288,7 +301,35 @@ __global__ void __launch_bounds__(128) flash_mma_kernel(Policy pol, AttnDims dm,
         mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
       }
     }
-    __syncthreads();   // every warp is done with this stage before it is refilled
+    group_sync();   // every warp of the group is done with this stage before it is refilled
+  }
+  if constexpr (KG == 2) {
+    // ---- merge the two key groups: group 1 parks (m, l, O) in shared memory, group 0 combines
+    __syncthreads();
+    float* xch = reinterpret_cast<float*>(KVbase) + (size_t)tid * (4 + HD / 2);
+    if (kg == 1) {
+      xch[0] = m_run[0]; xch[1] = m_run[1]; xch[2] = l_run[0]; xch[3] = l_run[1];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        xch[4 + 4 * i] = o[i][0]; xch[5 + 4 * i] = o[i][1]; xch[6 + 4 * i] = o[i][2]; xch[7 + 4 * i] = o[i][3];
+      }
+    }
+    __syncthreads();
+    if (kg == 1) return;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float m1 = xch[r], l1 = xch[2 + r];
+      const float mm = fmaxf(m_run[r], m1);
+      const float c0 = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] - mm);
+      const float c1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - mm);
+      l_run[r] = l_run[r] * c0 + l1 * c1;
+      m_run[r] = mm;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        o[i][2 * r] = o[i][2 * r] * c0 + xch[4 + 4 * i + 2 * r] * c1;
+        o[i][2 * r + 1] = o[i][2 * r + 1] * c0 + xch[5 + 4 * i + 2 * r] * c1;
+      }
+    }
   }
   // ---- epilogue
   if (dm.splits == 1) {
@@ -504,26 +545,34 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
 // ------------------------------------------------------------------------------------------------
 // host launchers used by the C-ABI entry points in attn_simt.cu
 // ------------------------------------------------------------------------------------------------
+template <typename T, int HD, typename Policy, int KG>
+static void launch_flash_kg(const Policy& pol, AttnDims dm, float* workspace, cudaStream_t st) {
+  constexpr size_t smem = sizeof(T) * (64 * (HD + 8) + (size_t)KG * 4 * 64 * (HD + 8)) + sizeof(unsigned long long) * 128;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(flash_mma_kernel<T, HD, Policy, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_mma_kernel<T, HD, Policy, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr_set = true;
+  }
+  dim3 grid(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
+  flash_mma_kernel<T, HD, Policy, KG><<<grid, 128 * KG, smem, st>>>(pol, dm, workspace);
+}
+
 template <typename T, typename Policy>
 static int launch_flash(const Policy& pol, AttnDims dm, int hd, float* workspace, cudaStream_t st, const char* what) {
-  dim3 grid(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
   PSALM_REQUIRE(dm.H <= 65535 && dm.B <= 65535, "%s: grid too large", what);
   PSALM_REQUIRE(dm.splits == 1 || workspace != nullptr, "%s: split-K needs a workspace", what);
   PSALM_REQUIRE(((dm.Lk + 63) / 64 + dm.splits - 1) / dm.splits <= 128,
                 "%s: more than 128 key tiles per split (Lk=%d, splits=%d): raise splits", what, dm.Lk, dm.splits);
-  static bool carveout_set = false;   // per (T, Policy) instantiation
-  if (!carveout_set) {
-    // 4 CTAs x 46 KB (HD = 64) per SM only fit if the L1/shared split favours shared memory; the driver's
-    // default carve-out left ONE CTA (4 warps) per SM (ncu: profiles/r1c_window_mma_ncu_details.txt)
-    cudaFuncSetAttribute(flash_mma_kernel<T, 32, Policy>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(flash_mma_kernel<T, 64, Policy>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    carveout_set = true;
-  }
+  // two key groups per CTA once a CTA would otherwise walk more than two key tiles
+  const bool kg2 = ((dm.Lk + 63) / 64 + dm.splits - 1) / dm.splits > 2;
   if (hd == 32) {
-    flash_mma_kernel<T, 32, Policy><<<grid, 128, 0, st>>>(pol, dm, workspace);
+    if (kg2) launch_flash_kg<T, 32, Policy, 2>(pol, dm, workspace, st);
+    else launch_flash_kg<T, 32, Policy, 1>(pol, dm, workspace, st);
     if (dm.splits > 1) flash_combine_kernel<Policy, 32><<<148 * 2, 256, 0, st>>>(pol, dm, workspace);
   } else if (hd == 64) {
-    flash_mma_kernel<T, 64, Policy><<<grid, 128, 0, st>>>(pol, dm, workspace);
+    if (kg2) launch_flash_kg<T, 64, Policy, 2>(pol, dm, workspace, st);
+    else launch_flash_kg<T, 64, Policy, 1>(pol, dm, workspace, st);
     if (dm.splits > 1) flash_combine_kernel<Policy, 64><<<148 * 2, 256, 0, st>>>(pol, dm, workspace);
   } else {
     set_error("%s: head_dim %d unsupported by the tensor-core path", what, hd);

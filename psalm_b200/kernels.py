@@ -88,7 +88,8 @@ def pick_splits(B, nh, Lq, Lk):
     """Split-K factor so that a 100-query problem still fills ~2 waves of 148 SMs."""
     ctas = B * nh * ((Lq + 63) // 64)
     want = max(1, (2 * 148 + ctas - 1) // ctas)
-    return int(max(1, min(want, (Lk + 127) // 128)))
+    # every CTA walks at least 4 key tiles of 64 (two per key group) so that the partial-result traffic stays small
+    return int(max(1, min(want, (Lk + 255) // 256)))
 
 
 def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, workspace=None):
