@@ -55,6 +55,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// 2^x on the SFU (MUFU.EX2), flush-to-zero: one instruction; exp2f() expands to range fix-ups around it.
+// ex2.approx(-inf) = +0, which is what the masked / first-tile cases rely on.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,6 +78,7 @@ struct CausalMma {
   __device__ __forceinline__ const T* ptr(int which, int b, int h, int n, int d0) const {
     return qkv + (((size_t)b * T_ + n) * 3 + which) * nh * hd + h * hd + d0;
   }
+  __device__ __forceinline__ size_t row_stride() const { return (size_t)3 * nh * hd; }   // elements between keys
   __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
     return ldg16(ptr(which, b, h, n, d0));
   }
@@ -103,6 +112,7 @@ struct CrossMma {
     const int L = which == 0 ? Lq : Lk;
     return base + ((size_t)b * L + n) * nh * hd + h * hd + d0;
   }
+  __device__ __forceinline__ size_t row_stride() const { return (size_t)nh * hd; }
   __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
     return ldg16(ptr(which, b, h, n, d0));
   }
@@ -186,14 +196,30 @@ __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Po
     if constexpr (KG == 1) __syncthreads();
     else asm volatile("bar.sync %0, 128;\n" ::"r"(1 + kg) : "memory");
   };
+  // each thread owns NSLOT fixed (row, 16-byte chunk) slots of the K and V tiles: global pointers are formed
+  // once and advanced by one tile stride per prefetch (no per-tile index arithmetic)
+  constexpr int NSLOT = BK * HD / 8 / 128;
+  const T* kbase = pol.ptr(1, b, h, 0, 0);
+  const long long vdelta = pol.ptr(2, b, h, 0, 0) - kbase;      // V sits at a fixed element offset from K
+  uint32_t goff[NSLOT];                                         // element offset of the slot inside a tile
+#pragma unroll
+  for (int j = 0; j < NSLOT; ++j) {
+    const int i = tid + 128 * j;
+    goff[j] = (uint32_t)((i / (HD / 8)) * (int)pol.row_stride() + (i % (HD / 8)) * 8);
+  }
+  const size_t tile_stride = (size_t)BK * pol.row_stride();
   auto prefetch = [&](int kt, int stage) {
-    for (int i = tid; i < BK * HD / 8; i += 128) {
-      const int row = i / (HD / 8), d0 = (i % (HD / 8)) * 8;
-      const int kj = kt * BK + row;
-      const bool ok = kj < dm.Lk;
-      const int kc = ok ? kj : 0;
-      cp_async16(&KVg[(stage * 2 + 0) * BK * LD + row * LD + d0], pol.ptr(1, b, h, kc, d0), ok ? 16 : 0);
-      cp_async16(&KVg[(stage * 2 + 1) * BK * LD + row * LD + d0], pol.ptr(2, b, h, kc, d0), ok ? 16 : 0);
+    const T* kt_base = kbase + (size_t)kt * tile_stride;
+    const int left = dm.Lk - kt * BK;   // keys of this tile that exist
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+      const int i = tid + 128 * j;
+      const int row = i / (HD / 8);
+      const int so = row * LD + (i % (HD / 8)) * 8;
+      const bool ok = row < left;
+      const T* src = ok ? kt_base + goff[j] : kbase;
+      cp_async16(&KVg[(stage * 2 + 0) * BK * LD + so], src, ok ? 16 : 0);
+      cp_async16(&KVg[(stage * 2 + 1) * BK * LD + so], src + vdelta, ok ? 16 : 0);
     }
     cp_async_commit();
   };
@@ -259,7 +285,7 @@ __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Po
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
       const float m_new = fmaxf(m_run[r], tmax[r]);
-      corr[r] = (m_new == -INFINITY) ? 1.f : exp2f(m_run[r] - m_new);   // exp2f(-inf) = 0 for the first tile
+      corr[r] = (m_new == -INFINITY) ? 1.f : fast_exp2(m_run[r] - m_new);   // exp2f(-inf) = 0 for the first tile
       msub[r] = (m_new == -INFINITY) ? 0.f : m_new;                     // avoids (-inf) - (-inf)
       m_run[r] = m_new;
     }
@@ -268,7 +294,7 @@ __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Po
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float p = exp2f(s[nt][e] - msub[e >> 1]);   // blocked: exp2f(-inf) = 0
+        const float p = fast_exp2(s[nt][e] - msub[e >> 1]);   // blocked: 2^(-inf) = 0
         s[nt][e] = p;
         psum[e >> 1] += p;
       }
@@ -499,8 +525,8 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     }
 #pragma unroll
     for (int nt = 0; nt < 18; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mx[0]); s[nt][1] = exp2f(s[nt][1] - mx[0]);
-      s[nt][2] = exp2f(s[nt][2] - mx[1]); s[nt][3] = exp2f(s[nt][3] - mx[1]);
+      s[nt][0] = fast_exp2(s[nt][0] - mx[0]); s[nt][1] = fast_exp2(s[nt][1] - mx[0]);
+      s[nt][2] = fast_exp2(s[nt][2] - mx[1]); s[nt][3] = fast_exp2(s[nt][3] - mx[1]);
       sum[0] += s[nt][0] + s[nt][1];
       sum[1] += s[nt][2] + s[nt][3];
     }
