@@ -125,3 +125,80 @@ def test_cuda_graph_replay_matches_eager():
         assert torch.equal(a[0]["panoptic_seg"][0], b[0]["panoptic_seg"][0]) and a[0]["panoptic_seg"][1] == b[0]["panoptic_seg"][1]
         assert torch.equal(a[0]["sem_seg"], b[0]["sem_seg"])
         assert torch.allclose(a[0]["instances"].scores, b[0]["instances"].scores, rtol=1e-5, atol=1e-7)
+
+
+def _oracle(sd, inp, task):
+    from oracle import psalm_oracle as O
+    phi = dict(hidden=256, layers=2, heads=4, inter=1024, eps=1e-5, theta=10000.0, rotary_frac=0.5)
+    with torch.no_grad():
+        return O.eval_seg(sd, inp["input_ids"], inp["attention_mask"], inp["images"], inp["seg_info"],
+                          class_name_ids=inp.get("class_name_ids"), cls_indices=inp.get("cls_indices"),
+                          class_name_embedding_indices=inp.get("class_name_embedding_indices"),
+                          token_refer_id=inp.get("token_refer_id"),
+                          refer_embedding_indices=inp.get("refer_embedding_indices"),
+                          is_thing_list=inp.get("is_thing_list"), task=task, phi_cfg=phi, return_intermediates=True)
+
+
+def _eval(m, inp):
+    kw = {k: inp[k] for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "token_refer_id",
+                              "refer_embedding_indices", "is_thing_list") if k in inp}
+    r = m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                   seg_info=inp["seg_info"], **kw)
+    torch.cuda.synchronize()
+    return r
+
+
+@pytest.mark.parametrize("task", ["instance", "semantic"])
+def test_other_tasks_fp32_vs_oracle(task):
+    """SEG_TASK instance / semantic (llava_phi.py:268-301) against the CPU oracle on the same weights."""
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=11)
+    inp = synth.synth_inputs(batch=1, height=160, width=224, task=task, n_classes=9, seed=12)
+    inp.pop("is_thing_list", None)
+    ores, it = _oracle(sd, inp, task)
+    res = _eval(PSALM(sd, SMALL, torch.float32, "cuda", task), inp)
+    if task == "semantic":
+        a, b = res[0]["sem_seg"].cpu(), ores[0]["sem_seg"]
+        assert a.shape == b.shape and (a - b).abs().max() / b.abs().max() < 1e-3
+    else:
+        sa = torch.sort(res[0]["instances"].scores.cpu(), descending=True).values
+        sb = torch.sort(ores[0]["instances"]["scores"], descending=True).values
+        assert torch.allclose(sa, sb, rtol=1e-3, atol=1e-5)
+        assert res[0]["instances"].pred_masks.shape == ores[0]["instances"]["pred_masks"].shape
+
+
+def test_padded_image_crop_and_resize_fp32_vs_oracle():
+    """seg_info with a real padding box and an output size different from the network input: exercises the
+    crop + bilinear resize of sem_seg_postprocess (llava_phi.py:1418-1430), not the fused fast path."""
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=21)
+    inp = synth.synth_inputs(batch=1, height=192, width=256, task="panoptic", n_classes=9, seed=22)
+    pm = torch.zeros(192, 256, dtype=torch.bool)
+    pm[150:, :] = True
+    pm[:, 200:] = True
+    inp["seg_info"] = [dict(padding_mask=pm, height=300, width=400)]
+    ores, it = _oracle(sd, inp, "panoptic")
+    for dtype, tol in ((torch.float32, 1e-3), (torch.bfloat16, 0.3)):
+        res = _eval(PSALM(sd, SMALL, dtype, "cuda", "panoptic"), inp)
+        a, b = res[0]["sem_seg"].float().cpu(), ores[0]["sem_seg"]
+        assert tuple(a.shape) == tuple(b.shape) == (8, 300, 400)
+        assert (a - b).norm() / b.norm() < tol
+        pa, pb = res[0]["panoptic_seg"][0].cpu(), ores[0]["panoptic_seg"][0]
+        assert pa.shape == pb.shape
+        if dtype == torch.float32:
+            assert (pa != pb).float().mean() < 2e-3 and res[0]["panoptic_seg"][1] == ores[0]["panoptic_seg"][1]
+
+
+def test_fused_task_heads_track_the_oracle_bf16():
+    """16-bit run with the fused task-head kernel (one image, no crop): semantic map and instance scores close
+    to the fp32 oracle, panoptic segment list identical when the fp32 decision margins are not marginal."""
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=0)
+    inp = synth.synth_inputs(batch=1, height=192, width=192, task="panoptic", n_classes=20, seed=1)
+    ores, it = _oracle(sd, inp, "panoptic")
+    m = PSALM(sd, SMALL, torch.bfloat16, "cuda", "panoptic")
+    assert m.fused_postprocess
+    res = _eval(m, inp)
+    a, b = res[0]["sem_seg"].float().cpu(), ores[0]["sem_seg"]
+    assert (a - b).norm() / b.norm() < 0.2
+    assert res[0]["instances"].pred_masks.shape[1:] == (192, 192)
