@@ -94,7 +94,10 @@ int psalm_window_attention(const void* qkv, const void* qkv_bias, const float* r
                            int B, int H, int W, int C, int nh, int ws, int shift, int dtype, void* stream);
 
 /* Attention implementation selector: 0 = auto (tensor-core kernels for fp16/bf16 storage, fp32 SIMT
- * kernels for fp32 storage), 1 = force the fp32-math SIMT kernels for every storage type (parity runs). */
+ * kernels for fp32 storage; split-K cross-attention with <= 4 splits reduces its partials inside a thread-block
+ * cluster over distributed shared memory, larger split counts go through the workspace + a combine kernel),
+ * 1 = force the fp32-math SIMT kernels for every storage type (parity runs), 2 / 3 = tensor-core kernels with
+ * the split-K reduction always through the workspace / always inside a cluster (<= 16 splits). */
 int psalm_set_attention_impl(int impl);
 
 /* Causal prefill attention of the LLM (third-party PhiAttention eager path; call site
@@ -165,9 +168,13 @@ int psalm_groupnorm_tokens(const void* x, const void* weight, const void* bias, 
  *   ids / in_mask [H,W]: arg-max_q (wq[q] * sigmoid + negq[q]) and (sigmoid >= 0.5 at the winner)
  *              (panoptic_inference, llava_phi.py:341-361; NULL x4 to skip)
  *   inst_masks [K,H,W] fp32 = (up(logits)[slot_query[k]] > 0); slots with query -1 are not written
- *   partials   [gx*gy, Q, 5] per-CTA sums: count(x>0), sum(sigmoid*[x>0]), count(x>=0), area, inter
- *              (gx, gy from psalm_postproc_grid); the caller reduces over the first axis. */
-int psalm_postproc_grid(int H, int W, int* gx, int* gy);
+ *   partials   [rows, Q, 5] per-CTA sums: count(x>0), sum(sigmoid*[x>0]), count(x>=0), area, inter
+ *              (rows from psalm_postproc_partials for the same arguments); the caller reduces over the first axis.
+ * Two kernels sit behind the call: a tensor-core formulation (16-bit logits, x1..x8 power-of-two up-sampling:
+ * up-sampling and the semantic einsum are both mma GEMMs, persistent CTAs) and a generic one (any dtype /
+ * resize factor).  psalm_set_postproc_impl: 0 = auto, 1 = generic, 2 = tensor-core (error if unsupported). */
+int psalm_set_postproc_impl(int impl);
+int psalm_postproc_partials(int Q, int H4, int W4, int H, int W, int ncls, int K, int dtype, int* rows);
 int psalm_postproc_fused(const void* logits, const void* probsT_f16, const float* wq, const float* negq,
                          const int* slot_query, float* sem_seg, float* inst_masks, int* ids,
                          unsigned char* in_mask, float* partials, int Q, int H4, int W4, int H, int W, int ncls,

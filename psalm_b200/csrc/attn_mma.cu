@@ -12,6 +12,8 @@
 // the accumulators, which TMEM round trips would not speed up; see DESIGN.md.)
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace psalm {
@@ -140,7 +142,9 @@ struct CrossMma {
 // own double-buffered K/V stages and named barrier, and the groups' (m, l, O) partials are merged through
 // shared memory at the end (intra-CTA split-K).  At T ~ 900 / 100 queries the kernel is bound by the
 // per-warp instruction latency of the longest CTA, so halving that CTA's tile count is what pays.
-template <typename T, int HD, typename Policy, int KG>
+// CL = the `splits` CTAs of one (query tile, head, batch) form a thread-block cluster and reduce their (m, l, O)
+// partials through distributed shared memory: no workspace round trip, no second launch.
+template <typename T, int HD, typename Policy, int KG, bool CL = false>
 __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Policy pol, AttnDims dm, float* __restrict__ part) {
   constexpr int BQ = 64, BK = 64, LD = HD + 8;
   extern __shared__ __align__(16) unsigned char flash_smem[];
@@ -341,7 +345,8 @@ __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Po
       }
     }
     __syncthreads();
-    if (kg == 1) return;
+    if (!CL && kg == 1) return;
+    if (kg == 0) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float m1 = xch[r], l1 = xch[2 + r];
@@ -356,8 +361,55 @@ __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Po
         o[i][2 * r + 1] = o[i][2 * r + 1] * c0 + xch[5 + 4 * i + 2 * r] * c1;
       }
     }
+    }
   }
   // ---- epilogue
+  if constexpr (CL) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int RW = HD + 2;                         // row of the exchange buffer: O[HD], m, l
+    float* red = reinterpret_cast<float*>(KVbase);     // [BQ][RW]; the K/V stages are dead by now
+    __syncthreads();                                   // (KG == 2: group 0 has consumed xch)
+    if (kg == 0) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float* pr = red + (warp * 16 + g + 8 * r) * RW;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          pr[i * 8 + 2 * t4] = o[i][2 * r];
+          pr[i * 8 + 2 * t4 + 1] = o[i][2 * r + 1];
+        }
+        if (t4 == 0) {
+          pr[HD] = m_run[r];
+          pr[HD + 1] = l_run[r];
+        }
+      }
+    }
+    cluster.sync();
+    // CTA `rank` finishes rows rank, rank + splits, ...: one thread per (row, channel)
+    const int rank = (int)cluster.block_rank(), nr = (int)cluster.num_blocks();
+    const int rows_mine = (BQ - rank + nr - 1) / nr;
+    for (int idx = threadIdx.x; idx < rows_mine * HD; idx += 128 * KG) {
+      const int row = rank + (idx / HD) * nr, d = idx % HD;
+      const int qi = q0 + row;
+      if (qi >= dm.Lq) continue;
+      float M = -INFINITY;
+      for (int s2 = 0; s2 < nr; ++s2) M = fmaxf(M, cluster.map_shared_rank(red, s2)[row * RW + HD]);
+      float L = 0.f, O = 0.f;
+      if (M != -INFINITY) {
+        for (int s2 = 0; s2 < nr; ++s2) {
+          const float* rr = cluster.map_shared_rank(red, s2) + row * RW;
+          const float ms = rr[HD];
+          const float e = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+          L += rr[HD + 1] * e;
+          O += rr[d] * e;
+        }
+      }
+      pol.store(b, h, qi, d, L > 0.f ? O / L : 0.f);
+    }
+    cluster.sync();   // nobody leaves while its shared memory may still be read remotely
+    return;
+  }
   if (dm.splits == 1) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -584,6 +636,53 @@ static void launch_flash_kg(const Policy& pol, AttnDims dm, float* workspace, cu
   flash_mma_kernel<T, HD, Policy, KG><<<grid, 128 * KG, smem, st>>>(pol, dm, workspace);
 }
 
+// cluster split-K: cluster = the `splits` CTAs of one (query tile, head, batch); returns false if the launch
+// configuration is not schedulable on this device (caller falls back to workspace + combine kernel)
+template <typename T, int HD, typename Policy, int KG>
+static bool launch_flash_cluster(const Policy& pol, AttnDims dm, cudaStream_t st) {
+  constexpr size_t smem = sizeof(T) * (64 * (HD + 8) + (size_t)KG * 4 * 64 * (HD + 8)) + sizeof(unsigned long long) * 128;
+  auto kern = flash_mma_kernel<T, HD, Policy, KG, true>;
+  static int max_cluster = -1;   // per instantiation: largest cluster size proven schedulable
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
+  cfg.blockDim = dim3(128 * KG);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = dm.splits;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (max_cluster < 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    max_cluster = 0;
+    for (int cs = 16; cs >= 2; cs >>= 1) {
+      cudaLaunchConfig_t probe = cfg;
+      cudaLaunchAttribute pa[1] = {at[0]};
+      pa[0].val.clusterDim.x = cs;
+      probe.gridDim = dim3(cs, 1, 1);
+      probe.attrs = pa;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &probe) == cudaSuccess && n > 0) {
+        max_cluster = cs;
+        break;
+      }
+    }
+    cudaGetLastError();   // a failed probe is not an error of the call
+  }
+  if (dm.splits > max_cluster) return false;
+  return cudaLaunchKernelEx(&cfg, kern, pol, dm, (float*)nullptr) == cudaSuccess;
+}
+
+// split-K reduction of the masked cross-attention: 0 = auto (thread-block cluster + DSMEM for <= 4 splits, where one
+// launch beats two; workspace + combine kernel above that: large clusters schedule slowly), 1 = always workspace,
+// 2 = always cluster (when schedulable).  Set through psalm_set_attention_impl.
+int g_splitk_mode = 0;
+
 template <typename T, typename Policy>
 static int launch_flash(const Policy& pol, AttnDims dm, int hd, float* workspace, cudaStream_t st, const char* what) {
   PSALM_REQUIRE(dm.H <= 65535 && dm.B <= 65535, "%s: grid too large", what);
@@ -592,6 +691,14 @@ static int launch_flash(const Policy& pol, AttnDims dm, int hd, float* workspace
                 "%s: more than 128 key tiles per split (Lk=%d, splits=%d): raise splits", what, dm.Lk, dm.splits);
   // two key groups per CTA once a CTA would otherwise walk more than two key tiles
   const bool kg2 = ((dm.Lk + 63) / 64 + dm.splits - 1) / dm.splits > 2;
+  if constexpr (!Policy::kCausal) {
+    // masked cross-attention (head_dim 32), split-K: reduce inside a thread-block cluster when it can be scheduled
+    if (hd == 32 && dm.splits > 1 && dm.splits <= 16 && (g_splitk_mode == 2 || (g_splitk_mode == 0 && dm.splits <= 4))) {
+      const bool ok = kg2 ? launch_flash_cluster<T, 32, Policy, 2>(pol, dm, st) : launch_flash_cluster<T, 32, Policy, 1>(pol, dm, st);
+      if (ok) return check_launch(what);
+      cudaGetLastError();
+    }
+  }
   if (hd == 32) {
     if (kg2) launch_flash_kg<T, 32, Policy, 2>(pol, dm, workspace, st);
     else launch_flash_kg<T, 32, Policy, 1>(pol, dm, workspace, st);

@@ -327,14 +327,16 @@ int mma_cross_attention(const void*, const void*, const void*, const uint32_t*, 
                         int, int, int, int, int, int, cudaStream_t);
 int mma_window_attention(const void*, const void*, const float*, void*, int, int, int, int, int, int, int,
                          cudaStream_t);
+extern int g_splitk_mode;
 static int g_attn_impl = 0;  // 0 = auto (tensor cores for 16-bit storage), 1 = force the fp32 SIMT kernels
 }  // namespace psalm
 
 using namespace psalm;
 
 extern "C" int psalm_set_attention_impl(int impl) {
-  PSALM_REQUIRE(impl == 0 || impl == 1, "set_attention_impl: 0 (auto) or 1 (simt)");
-  g_attn_impl = impl;
+  PSALM_REQUIRE(impl >= 0 && impl <= 3, "set_attention_impl: 0 (auto), 1 (simt), 2 (split-K via workspace) or 3 (split-K via cluster)");
+  g_attn_impl = impl == 1 ? 1 : 0;
+  g_splitk_mode = impl == 2 ? 1 : (impl == 3 ? 2 : 0);
   return PSALM_OK;
 }
 

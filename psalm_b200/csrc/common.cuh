@@ -65,6 +65,16 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// packed fp32 FMA (Blackwell FFMA2): acc.xy += v.xy * w
+__device__ __forceinline__ void ffma2(float2& acc, const float2 v, const float w) {
+  unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
+  const unsigned long long b = *reinterpret_cast<const unsigned long long*>(&v);
+  const float2 ww = make_float2(w, w);
+  const unsigned long long c = *reinterpret_cast<const unsigned long long*>(&ww);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(b), "l"(c));
+  acc = *reinterpret_cast<float2*>(&a);
+}
+
 // 16-byte vector of CH elements of T (CH = 4 for fp32, 8 for 16-bit types), as fp32 lanes
 template <typename T> struct Vec16 {
   static constexpr int CH = 16 / sizeof(T);
@@ -81,6 +91,22 @@ __device__ __forceinline__ void load16_as_f32(const T* p, float (&f)[16 / sizeof
     unpack2<T>(v.y, f[2], f[3]);
     unpack2<T>(v.z, f[4], f[5]);
     unpack2<T>(v.w, f[6], f[7]);
+  }
+}
+
+// same, as CH/2 float2 pairs (operands of the packed FFMA2 path)
+template <typename T>
+__device__ __forceinline__ void load16_as_f32x2(const T* p, float2 (&f)[8 / sizeof(T)]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = make_float2(v.x, v.y);
+    f[1] = make_float2(v.z, v.w);
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack2<T>(v.x, f[0].x, f[0].y);
+    unpack2<T>(v.y, f[1].x, f[1].y);
+    unpack2<T>(v.z, f[2].x, f[2].y);
+    unpack2<T>(v.w, f[3].x, f[3].y);
   }
 }
 

@@ -340,9 +340,9 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
   }
 
   const TV* __restrict__ vb = value + ((size_t)b * M + m) * (size_t)S * DC + cl * CH;
-  float acc[CH];
+  float2 acc2[CH / 2];   // accumulated with packed FFMA2: half the FMA issue slots of scalar FFMA
 #pragma unroll
-  for (int i = 0; i < CH; ++i) acc[i] = 0.f;
+  for (int i = 0; i < CH / 2; ++i) acc2[i] = make_float2(0.f, 0.f);
 
 #pragma unroll
   for (int s = 0; s < LP; ++s) {
@@ -355,18 +355,24 @@ msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ o
     const float w01 = __shfl_sync(0xffffffffu, pw[j][1], owner);
     const float w10 = __shfl_sync(0xffffffffu, pw[j][2], owner);
     const float w11 = __shfl_sync(0xffffffffu, pw[j][3], owner);
-    float f00[CH], f01[CH], f10[CH], f11[CH];
-    load16_as_f32<TV>(vb + o00, f00);
-    load16_as_f32<TV>(vb + o01, f01);
-    load16_as_f32<TV>(vb + o10, f10);
-    load16_as_f32<TV>(vb + o11, f11);
+    float2 f00[CH / 2], f01[CH / 2], f10[CH / 2], f11[CH / 2];
+    load16_as_f32x2<TV>(vb + o00, f00);
+    load16_as_f32x2<TV>(vb + o01, f01);
+    load16_as_f32x2<TV>(vb + o10, f10);
+    load16_as_f32x2<TV>(vb + o11, f11);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      acc[i] = fmaf(w00, f00[i], acc[i]);
-      acc[i] = fmaf(w01, f01[i], acc[i]);
-      acc[i] = fmaf(w10, f10[i], acc[i]);
-      acc[i] = fmaf(w11, f11[i], acc[i]);
+    for (int i = 0; i < CH / 2; ++i) {
+      ffma2(acc2[i], f00[i], w00);
+      ffma2(acc2[i], f01[i], w01);
+      ffma2(acc2[i], f10[i], w10);
+      ffma2(acc2[i], f11[i], w11);
     }
+  }
+  float acc[CH];
+#pragma unroll
+  for (int i = 0; i < CH / 2; ++i) {
+    acc[2 * i] = acc2[i].x;
+    acc[2 * i + 1] = acc2[i].y;
   }
   if (active) store16_from_f32<TV>(out + (((size_t)b * S + q) * M + m) * (size_t)DC + cl * CH, acc);
 }

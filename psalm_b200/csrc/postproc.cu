@@ -224,11 +224,39 @@ constexpr size_t pp_smem_bytes() {
 
 }  // namespace psalm
 
+namespace psalm {
+// postproc_fast.cu
+bool postproc_fast_ok(int Q, int H4, int W4, int H, int W, int ncls, int K, int dtype);
+int postproc_fast_ctas(int H, int W);
+int postproc_fast_launch(const void* logits, const void* probsT_f16, const float* wq, const float* negq,
+                         const int* slot_query, float* sem_seg, float* inst_masks, int* ids, unsigned char* in_mask,
+                         float* partials, int Q, int H4, int W4, int H, int W, int ncls, int K, int dtype,
+                         cudaStream_t st);
+}  // namespace psalm
+
 using namespace psalm;
 
-extern "C" int psalm_postproc_grid(int H, int W, int* gx, int* gy) {
-  *gx = (W + PP_TW - 1) / PP_TW;
-  *gy = (H + PP_TH - 1) / PP_TH;
+static int g_postproc_impl = 0;   // 0 auto, 1 generic SIMT-blend kernel, 2 tensor-core kernel
+
+extern "C" int psalm_set_postproc_impl(int impl) {
+  PSALM_REQUIRE(impl >= 0 && impl <= 2, "set_postproc_impl: 0 (auto), 1 (generic) or 2 (tensor-core)");
+  g_postproc_impl = impl;
+  return PSALM_OK;
+}
+
+static bool use_fast(int Q, int H4, int W4, int H, int W, int ncls, int K, int dtype) {
+  return g_postproc_impl != 1 && postproc_fast_ok(Q, H4, W4, H, W, ncls, K, dtype);
+}
+
+extern "C" int psalm_postproc_partials(int Q, int H4, int W4, int H, int W, int ncls, int K, int dtype, int* rows) {
+  PSALM_REQUIRE(rows && H > 0 && W > 0, "postproc_partials: bad arguments");
+  if (g_postproc_impl == 2 && !postproc_fast_ok(Q, H4, W4, H, W, ncls, K, dtype)) {
+    set_error("postproc_partials: tensor-core path forced but unsupported (needs 16-bit logits, x1..x8 power-of-two "
+              "up-sampling, Q <= 112, ncls <= 144)");
+    return PSALM_E_ARG;
+  }
+  *rows = use_fast(Q, H4, W4, H, W, ncls, K, dtype) ? postproc_fast_ctas(H, W)
+                                                     : ((W + PP_TW - 1) / PP_TW) * ((H + PP_TH - 1) / PP_TH);
   return PSALM_OK;
 }
 
@@ -237,11 +265,16 @@ extern "C" int psalm_postproc_fused(const void* logits, const void* probsT_f16, 
                                     unsigned char* in_mask, float* partials, int Q, int H4, int W4, int H, int W,
                                     int ncls, int K, int dtype, void* stream) {
   PSALM_REQUIRE(logits && partials, "postproc_fused: null pointer");
-  PSALM_REQUIRE(Q > 0 && Q <= 104 && ncls <= PP_CP, "postproc_fused: Q=%d (max 104) / ncls=%d (max %d) unsupported", Q, ncls, PP_CP);
   PSALM_REQUIRE((probsT_f16 == nullptr) == (sem_seg == nullptr), "postproc_fused: probsT and sem_seg go together");
   PSALM_REQUIRE((wq == nullptr) == (ids == nullptr) && (wq == nullptr) == (negq == nullptr) && (wq == nullptr) == (in_mask == nullptr),
                 "postproc_fused: wq / negq / ids / in_mask go together");
   PSALM_REQUIRE((slot_query == nullptr) == (inst_masks == nullptr), "postproc_fused: slot_query and inst_masks go together");
+  if (g_postproc_impl == 2)
+    PSALM_REQUIRE(postproc_fast_ok(Q, H4, W4, H, W, ncls, K, dtype), "postproc_fused: tensor-core path forced but unsupported");
+  if (use_fast(Q, H4, W4, H, W, ncls, K, dtype))
+    return postproc_fast_launch(logits, probsT_f16, wq, negq, slot_query, sem_seg, inst_masks, ids, in_mask, partials,
+                                Q, H4, W4, H, W, ncls, K, dtype, (cudaStream_t)stream);
+  PSALM_REQUIRE(Q > 0 && Q <= 104 && ncls <= PP_CP, "postproc_fused: Q=%d (max 104) / ncls=%d (max %d) unsupported", Q, ncls, PP_CP);
   // source taps per tile must fit the shared-memory window: (TH*scale + 2) x (TW*scale + 2)
   const float sh = (float)H4 / (float)H, sw = (float)W4 / (float)W;
   const int SR = (int)(PP_TH * sh) + 3, SC = (int)(PP_TW * sw) + 3;

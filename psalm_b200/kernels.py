@@ -89,7 +89,8 @@ def pick_splits(B, nh, Lq, Lk):
     ctas = B * nh * ((Lq + 63) // 64)
     want = max(1, (2 * 148 + ctas - 1) // ctas)
     # every CTA walks at least 4 key tiles of 64 (two per key group) so that the partial-result traffic stays small
-    return int(max(1, min(want, (Lk + 255) // 256)))
+    # <= 16: the split-K partials are reduced inside one thread-block cluster (distributed shared memory)
+    return int(max(1, min(want, (Lk + 255) // 256, 16)))
 
 
 def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, workspace=None):
@@ -211,9 +212,11 @@ def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=Non
     _chk(logits, "postproc_fused.logits")
     Q, H4, W4 = logits.shape
     dev = logits.device
-    gx, gy = ctypes.c_int(), ctypes.c_int()
-    _lib.lib().psalm_postproc_grid(H, W, ctypes.byref(gx), ctypes.byref(gy))
-    partials = torch.empty((gx.value * gy.value, Q, 5), dtype=torch.float32, device=dev)
+    K = 0 if slot_query is None else slot_query.shape[0]
+    rows = ctypes.c_int()
+    _lib.check(_lib.lib().psalm_postproc_partials(Q, H4, W4, H, W, ncls, K, _lib.dtype_code(logits.dtype), ctypes.byref(rows)),
+               "psalm_postproc_partials")
+    partials = torch.empty((rows.value, Q, 5), dtype=torch.float32, device=dev)
     out = {}
     sem = ids = inm = inst = None
     if probsT is not None:

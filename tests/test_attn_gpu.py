@@ -11,11 +11,13 @@ DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 TOL = {"f32": 2e-5, "f16": 2e-3, "bf16": 1.2e-2}   # max |err| / max |ref|; 16-bit = output rounding
 
 
-@pytest.fixture(params=["auto", "simt"], autouse=True)
+@pytest.fixture(params=["auto", "simt", "mma-workspace", "mma-cluster"], autouse=True)
 def attn_impl(request):
-    """auto = tensor-core (mma.sync) kernels for fp16/bf16 + SIMT for fp32; simt = fp32-math kernels for all."""
+    """auto = tensor-core (mma.sync) kernels for fp16/bf16 + SIMT for fp32; simt = fp32-math kernels for all;
+    mma-workspace / mma-cluster = tensor cores with the split-K reduction forced through the workspace + combine
+    kernel / through a thread-block cluster (distributed shared memory)."""
     from psalm_b200 import _lib
-    _lib.check(_lib.lib().psalm_set_attention_impl(1 if request.param == "simt" else 0), "set_attention_impl")
+    _lib.check(_lib.lib().psalm_set_attention_impl({"auto": 0, "simt": 1, "mma-workspace": 2, "mma-cluster": 3}[request.param]), "set_attention_impl")
     yield request.param
     _lib.lib().psalm_set_attention_impl(0)
 
@@ -63,7 +65,9 @@ def test_rotary_and_causal_attention(dt, T, padded):
 
 
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
-@pytest.mark.parametrize("Lq,Lk,splits", [(100, 1024, None), (100, 4096, 4), (100, 389, 3), (37, 100, 1), (100, 100, 1)])
+@pytest.mark.parametrize("Lq,Lk,splits", [(100, 1024, None), (100, 4096, 4), (100, 389, 3), (37, 100, 1), (100, 100, 1),
+                                          (100, 4096, 16), (100, 16384, None), (100, 4096, 19), (100, 2048, 8),
+                                          (100, 700, 2), (64, 4096, 5)])
 def test_cross_attention_with_bit_mask(dt, Lq, Lk, splits):
     torch.manual_seed(Lq + Lk)
     B, nh, hd = 2, 8, 32

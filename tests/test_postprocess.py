@@ -82,3 +82,78 @@ def test_fused_kernel_gpu(task, dt, shape):
                                seg.cuda() if task == "referring" else None, thing, task in ("semantic", "panoptic"),
                                task in ("instance", "panoptic"), task == "panoptic", task == "referring")
     _compare(ref, got, task, 3e-3)
+
+
+def _set_impl(impl):
+    from psalm_b200 import _lib
+    _lib.check(_lib.lib().psalm_set_postproc_impl(impl), "psalm_set_postproc_impl")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(24, 40, 96, 160), (50, 66, 200, 264), (25, 33, 100, 132), (12, 20, 96, 160),
+                                   (64, 64, 256, 256)])
+@pytest.mark.parametrize("Q,ncls", [(100, 133), (37, 20), (112, 144)])
+def test_tensor_core_kernel_vs_generic_gpu(dt, shape, Q, ncls):
+    """The tensor-core formulation (csrc/postproc_fast.cu) against the torch restatement of the op and against the
+    generic kernel: exact integer outputs (counts, ids, instance masks) away from fp ties, fp sums to 1e-5."""
+    from psalm_b200 import kernels
+    H4, W4, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    logits = (torch.randn(Q, H4, W4, generator=g) * 4).to(dt)
+    logits[:, ::5, ::3] = 0          # exact zeros: (x >= 0) differs from (x > 0)
+    logits[3] = 0
+    probs = F.softmax(torch.randn(Q, ncls + 1, generator=g) * 3, -1)[:, :-1]
+    probsT = torch.zeros(144, 112, dtype=torch.float16)
+    probsT[:ncls, :Q] = probs.t().half()
+    keep = torch.rand(Q, generator=g) > 0.5
+    wq = torch.where(keep, torch.rand(Q, generator=g), torch.zeros(Q))
+    negq = keep.float() - 1
+    slots = torch.randint(-1, Q, (100,), generator=g).to(torch.int32)
+    ref = emu.postproc_fused(logits, H, W, probsT, wq, negq, slots, ncls)
+    outs = {}
+    try:
+        for impl in (1, 2):
+            if impl == 1 and Q > 104:
+                continue
+            _set_impl(impl)
+            outs[impl] = kernels.postproc_fused(logits.cuda(), H, W, probsT.cuda(), wq.cuda(), negq.cuda(), slots.cuda(), ncls)
+            again = kernels.postproc_fused(logits.cuda(), H, W, probsT.cuda(), wq.cuda(), negq.cuda(), slots.cuda(), ncls)
+            for k in ("sem_seg", "ids", "in_mask", "stats"):
+                assert torch.equal(outs[impl][k], again[k]), (impl, k)      # run-to-run deterministic
+    finally:
+        _set_impl(0)
+    x = F.interpolate(logits.float()[None], size=(H, W), mode="bilinear", align_corners=False)[0]
+    for impl, o in outs.items():
+        st = o["stats"].cpu()
+        # counts: the blend is exact up to fp32 summation order, so only |x| ~ 1e-7 pixels may flip
+        near = (x.abs() < 1e-5) & (x != 0)
+        slack = near.flatten(1).sum(1).float()
+        assert ((st[:, 0] - ref["stats"][:, 0]).abs() <= slack).all(), impl
+        assert ((st[:, 2] - ref["stats"][:, 2]).abs() <= slack).all(), impl
+        assert torch.allclose(st[:, 1], ref["stats"][:, 1], rtol=1e-3 if impl == 1 else 2e-5, atol=1e-2), impl
+        sem_err = (o["sem_seg"].cpu() - ref["sem_seg"]).abs().max() / ref["sem_seg"].abs().max()
+        assert sem_err < 2e-3, (impl, sem_err)
+        mism = (o["ids"].cpu() != ref["ids"]).float().mean()
+        assert mism < 1e-4, (impl, mism)
+        same = o["ids"].cpu() == ref["ids"]
+        assert ((o["in_mask"].cpu() != ref["in_mask"]) & same & ~near.any(0)).sum() == 0, impl
+        assert torch.equal(st[:, 3].sum(), torch.tensor(float(H * W))), impl
+        valid = slots >= 0
+        bad = (o["inst_masks"].cpu()[valid] != ref["inst_masks"][valid]).flatten(1).sum(1).float()
+        assert (bad <= slack[slots[valid].long()]).all(), impl
+    if 1 in outs and 2 in outs:
+        assert torch.equal(outs[1]["ids"], outs[2]["ids"]) or (outs[1]["ids"] != outs[2]["ids"]).float().mean() < 1e-5
+        assert torch.allclose(outs[1]["stats"][:, [0, 2]], outs[2]["stats"][:, [0, 2]], atol=2)
+
+
+@pytest.mark.gpu
+def test_tensor_core_path_forced_unsupported_raises():
+    from psalm_b200 import kernels, _lib
+    logits = torch.randn(10, 13, 21, device="cuda")      # fp32: tensor-core path unsupported
+    try:
+        _set_impl(2)
+        with pytest.raises(_lib.PsalmKernelError):
+            kernels.postproc_fused(logits, 61, 85)
+    finally:
+        _set_impl(0)
