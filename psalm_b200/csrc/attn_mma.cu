@@ -174,13 +174,12 @@ __global__ void __launch_bounds__(128 * KG, KG == 2 ? 2 : 4) flash_mma_kernel(Po
     if (q0 + row < dm.Lq) v = pol.load8(0, b, h, q0 + row, d0);
     *reinterpret_cast<uint4*>(&Qs[row * LD + d0]) = v;
   }
-  for (int t = kt0 + (int)threadIdx.x; t < kt1; t += 128 * KG) {
-    unsigned long long m = 0ull;
-    for (int j = 0; j < BK; ++j) {
-      const int kj = t * BK + j;
-      if (kj >= dm.Lk || pol.key_invalid(b, kj)) m |= 1ull << j;
-    }
-    kvbits[t - kt0] = m;
+  // invalid-key bits of every tile this CTA walks: one warp per tile, two keys per lane, two ballots
+  for (int t = kt0 + (int)(threadIdx.x >> 5); t < kt1; t += 4 * KG) {
+    const int k0 = t * BK + lane, k1 = k0 + 32;
+    const uint32_t lo = __ballot_sync(0xffffffffu, k0 >= dm.Lk || pol.key_invalid(b, k0));
+    const uint32_t hi = __ballot_sync(0xffffffffu, k1 >= dm.Lk || pol.key_invalid(b, k1));
+    if (lane == 0) kvbits[t - kt0] = ((unsigned long long)hi << 32) | lo;
   }
   __syncthreads();
   uint32_t qa[HD / 16][4];

@@ -23,7 +23,7 @@ constexpr int PF_CP = 144;            // classes padded to 18 n-tiles
 constexpr int PF_TR = 4, PF_TC = 8;   // source window slots per tile (rows x columns)
 constexpr int PF_TAPS = PF_TR * PF_TC;   // K of the up-sampling GEMM (tap = row * 8 + column)
 constexpr int PF_SLD = PF_TAPS + 8;   // source row stride (elements): 80 B rows, conflict-free ldmatrix
-constexpr int PF_NLD = 7;             // source registers staged per thread (two taps each)
+constexpr int PF_NLD = 7;             // 4-byte source pieces staged per thread
 constexpr int PF_ALD = PF_QP + 8;     // class-probability row stride (halfs)
 constexpr int PF_NV = 56;             // accumulator values per thread (14 n-tiles x 4)
 constexpr int PF_KMAX = 256;          // instance slots kept in shared memory
@@ -83,45 +83,55 @@ __device__ __forceinline__ PfTile pf_tile(const PostprocFastArgs& a, int tile, f
   t.tx0 = txi * PF_TW;
   const int ylast = min(t.ty0 + PF_TH, a.H) - 1, xlast = min(t.tx0 + PF_TW, a.W) - 1;
   t.sy0 = (int)pf_srcf(sh, t.ty0);
-  t.sx0 = (int)pf_srcf(sw, t.tx0);
+  t.sx0 = (int)pf_srcf(sw, t.tx0) & ~1;   // even start: the window is staged in aligned 4-byte pieces
   const int sy1 = min((int)pf_srcf(sh, ylast) + 1, a.H4 - 1), sx1 = min((int)pf_srcf(sw, xlast) + 1, a.W4 - 1);
   t.SR = sy1 - t.sy0 + 1;
   t.SC = sx1 - t.sx0 + 1;
   return t;
 }
 
-// source taps of one tile: thread -> (tap slots 2 (tid & 15), +1; queries (tid >> 4) + 16 k); each register carries
-// two adjacent taps of one query so the prefetch costs 7 registers
+// source taps of one tile -> shared memory ([query][tap slot], the [n][k] storage of the B operand), asynchronously:
+// thread -> (tap slots 2 (tid & 15), +1; queries (tid >> 4) + 16 k), one 4-byte cp.async each (zero-filled where the
+// slot lies outside the window or the query does not exist)
 template <typename T>
-__device__ __forceinline__ void pf_load_src(const PostprocFastArgs& a, const PfTile& t, int tid, uint32_t (&v)[PF_NLD]) {
+__device__ __forceinline__ void pf_stage_src(const PostprocFastArgs& a, const PfTile& t, int tid, T* dst) {
   const int tp = tid & 15, q0 = tid >> 4;
   const int ty = tp >> 2, tx = (tp & 3) * 2;
-  const bool ok0 = ty < t.SR && tx < t.SC, ok1 = ty < t.SR && tx + 1 < t.SC;
+  const int nb = ty < t.SR ? (tx + 1 < t.SC ? 4 : (tx < t.SC ? 2 : 0)) : 0;   // bytes of this piece that exist
   const size_t plane = (size_t)a.H4 * a.W4;
-  const unsigned short* p = reinterpret_cast<const unsigned short*>(a.logits) + (size_t)q0 * plane +
-                            (size_t)(t.sy0 + ty) * a.W4 + (t.sx0 + tx);
+  const T* p = reinterpret_cast<const T*>(a.logits) + (size_t)q0 * plane + (size_t)(t.sy0 + ty) * a.W4 + (t.sx0 + tx);
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + q0 * PF_SLD + 2 * tp);
 #pragma unroll
   for (int k = 0; k < PF_NLD; ++k) {
-    const bool qok = q0 + 16 * k < a.Q;
-    const uint32_t lo = (ok0 && qok) ? (uint32_t)__ldg(p + (size_t)k * 16 * plane) : 0u;
-    const uint32_t hi = (ok1 && qok) ? (uint32_t)__ldg(p + (size_t)k * 16 * plane + 1) : 0u;
-    v[k] = lo | (hi << 16);
+    const int n = (q0 + 16 * k < a.Q) ? nb : 0;
+    const T* src = n ? p + (size_t)k * 16 * plane : reinterpret_cast<const T*>(a.logits);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d + (uint32_t)(k * 16 * PF_SLD * sizeof(T))), "l"(src), "r"(n));
   }
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+
+// sigmoid on the SFU: ex2 + rcp (2 ulp), no range fix-ups (x is a finite logit)
+__device__ __forceinline__ float pf_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFastArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* As = reinterpret_cast<__half*>(smem_raw);                                  // [PF_CP][PF_ALD]
-  T* srcs = reinterpret_cast<T*>(As + PF_CP * PF_ALD);                               // [PF_QP][PF_SLD]
-  uint32_t* bal_pos = reinterpret_cast<uint32_t*>(srcs + PF_QP * PF_SLD);            // [8 warps][PF_NV]
+  T* srcs2 = reinterpret_cast<T*>(As + PF_CP * PF_ALD);                              // [2 stages][PF_QP][PF_SLD]
+  uint32_t* bal_pos = reinterpret_cast<uint32_t*>(srcs2 + 2 * PF_QP * PF_SLD);       // [8 warps][PF_NV]
   uint32_t* bal_ge = bal_pos + 8 * PF_NV;                                            // [8][PF_NV]
   int* ps_acc = reinterpret_cast<int*>(bal_ge + 8 * PF_NV);                          // [28][256] fixed-point partial sums
   float* wqs = reinterpret_cast<float*>(ps_acc + 28 * PF_THREADS);                   // [PF_QP]
   float* nqs = wqs + PF_QP;                                                          // [PF_QP]
   int* area_s = reinterpret_cast<int*>(nqs + PF_QP);                                 // [PF_QP]
   int* inter_s = area_s + PF_QP;                                                     // [PF_QP]
-  int* slots = inter_s + PF_QP;                                                      // [PF_KMAX]
+  int* slots = inter_s + PF_QP;                                                      // [PF_KMAX] packed ballot coordinates
+  int* zflag = slots + PF_KMAX;                                                      // [8] warp saw an exact zero logit
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -141,26 +151,27 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
     area_s[i] = 0;
     inter_s[i] = 0;
   }
-  for (int i = tid; i < PF_KMAX; i += PF_THREADS) slots[i] = (inst && i < a.K) ? a.slot_query[i] : -1;
+  for (int i = tid; i < PF_KMAX; i += PF_THREADS) {
+    // query -> where its bits sit in a warp's ballots: word (q >> 3) * 4 + (q & 1) (+ 2 for pixels 8..15), lane column (q & 7) >> 1
+    const int q = (inst && i < a.K) ? a.slot_query[i] : -1;
+    slots[i] = q < 0 ? -1 : (((q >> 3) * 4 + (q & 1)) | (((q & 7) >> 1) << 8));
+  }
 #pragma unroll
   for (int i = 0; i < 28; ++i) ps_acc[i * PF_THREADS + tid] = 0;
   int cnt_tot = 0, ge_tot = 0;   // thread q < Q: running count(x > 0), count(x >= 0)
 
-  uint32_t nxt[PF_NLD];
-  int tile = blockIdx.x;
+  int tile = blockIdx.x, it = 0;
   PfTile tl = pf_tile(a, tile < a.ntiles ? tile : 0, sh, sw);
-  if (tile < a.ntiles) pf_load_src<T>(a, tl, tid, nxt);
+  if (tile < a.ntiles) pf_stage_src<T>(a, tl, tid, srcs2);
 
-  for (; tile < a.ntiles; tile += gridDim.x) {
-    // ---- source window -> shared memory ([query][tap], the [n][k] storage of the B operand)
-#pragma unroll
-    for (int k = 0; k < PF_NLD; ++k)
-      *reinterpret_cast<uint32_t*>(&srcs[((tid >> 4) + 16 * k) * PF_SLD + 2 * (tid & 15)]) = nxt[k];
-    __syncthreads();
+  for (; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const T* srcs = srcs2 + (it & 1) * PF_QP * PF_SLD;
+    asm volatile("cp.async.wait_all;\n" ::);
+    __syncthreads();   // this tile's window has landed; every warp is done with the previous tile's buffers
     const PfTile cur = tl;
-    if (tile + (int)gridDim.x < a.ntiles) {   // prefetch the next tile's taps behind this tile's math
+    if (tile + (int)gridDim.x < a.ntiles) {   // next tile's window streams in behind this tile's math
       tl = pf_tile(a, tile + gridDim.x, sh, sw);
-      pf_load_src<T>(a, tl, tid, nxt);
+      pf_stage_src<T>(a, tl, tid, srcs2 + ((it + 1) & 1) * PF_QP * PF_SLD);
     }
 
     // ---- A operand: bilinear weights of this warp's 16 pixels (tile row `warp`) over the 16 taps
@@ -215,13 +226,26 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
     // x == 0 exactly is the only case where (x >= 0) and (x > 0) differ: detect it once per warp
     float mn = 1.f;
 #pragma unroll
-    for (int j = 0; j < 14; ++j)
+    for (int j = 0; j < 14; ++j) {
+      if (8 * j + 8 <= Q) {   // whole n-tile holds real queries (warp-uniform)
+        mn = fminf(fminf(mn, fabsf(xs[j][0])), fminf(fabsf(xs[j][1]), fminf(fabsf(xs[j][2]), fabsf(xs[j][3]))));
+      } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool qok = 8 * j + 2 * t4 + (c & 1) < Q;
-        mn = qok ? fminf(mn, fabsf(xs[j][c])) : mn;
+        for (int c = 0; c < 4; ++c) mn = (8 * j + 2 * t4 + (c & 1) < Q) ? fminf(mn, fabsf(xs[j][c])) : mn;
       }
+    }
     const bool has_zero = __any_sync(0xffffffffu, mn == 0.f);
+    if (lane == 0) zflag[warp] = has_zero;
+    if (has_zero) {   // rare: (x >= 0) ballots differ from the (x > 0) ones
+#pragma unroll
+      for (int j = 0; j < 14; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t bg = __ballot_sync(0xffffffffu, ((c < 2) ? inb0 : inb1) && xs[j][c] >= 0.f);
+          if (lane == 0) bal_ge[warp * PF_NV + j * 4 + c] = bg;
+        }
+    }
+    const uint32_t* bal_gew = has_zero ? bal_ge : bal_pos;   // this warp's (x >= 0) ballots
 
     float bv0 = -2.f, bv1 = -2.f;
     int bq0 = 0, bq1 = 0;
@@ -233,21 +257,15 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
         n2 = *reinterpret_cast<const float2*>(&nqs[8 * j + 2 * t4]);
       }
       int fix[4];
+      uint32_t bp[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float x = xs[j][c];
-        const bool ib = (c < 2) ? inb0 : inb1;
-        const float s = __fdividef(1.f, 1.f + __expf(-x));
-        const bool pos = ib && x > 0.f;
-        const uint32_t bp = __ballot_sync(0xffffffffu, pos);
-        uint32_t bg = bp;
-        if (has_zero) bg = __ballot_sync(0xffffffffu, ib && x >= 0.f);
-        if (lane == 0) {
-          bal_pos[warp * PF_NV + j * 4 + c] = bp;
-          bal_ge[warp * PF_NV + j * 4 + c] = bg;
-        }
-        // s + 2 lies in [2, 3]: its mantissa is round(s * 2^22)
-        fix[c] = pos ? (__float_as_int(s + 2.0f) & 0x7fffff) : 0;
+        const float s = pf_sigmoid(x);
+        const bool pos = ((c < 2) ? inb0 : inb1) && x > 0.f;
+        bp[c] = __ballot_sync(0xffffffffu, pos);
+        // (pos ? s : 0) + 2 lies in [2, 3]: its bit pattern is 0x40000000 + round(s * 2^22)
+        fix[c] = __float_as_int((pos ? s : 0.f) + 2.0f);
         if (pan) {
           const float v = fmaf((c & 1) ? w2.y : w2.x, s, (c & 1) ? n2.y : n2.x);
           const int q = 8 * j + 2 * t4 + (c & 1);
@@ -256,9 +274,11 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
         }
         xs[j][c] = s;
       }
-      // own slot, integer add: exact and order-independent (at most 2^23 per tile, <= 255 tiles per CTA)
-      ps_acc[(2 * j) * PF_THREADS + tid] += fix[0] + fix[2];
-      ps_acc[(2 * j + 1) * PF_THREADS + tid] += fix[1] + fix[3];
+      if (lane == 0) *reinterpret_cast<uint4*>(&bal_pos[warp * PF_NV + j * 4]) = make_uint4(bp[0], bp[1], bp[2], bp[3]);
+      // own slot, wrapping integer add: exact and order-independent.  Every add carries 2 * 0x40000000 = 2^31 of
+      // exponent bits, removed at the end from the number of tiles; the payload is at most 2^23 per tile.
+      atomicAdd(reinterpret_cast<unsigned int*>(&ps_acc[(2 * j) * PF_THREADS + tid]), (unsigned int)fix[0] + (unsigned int)fix[2]);
+      atomicAdd(reinterpret_cast<unsigned int*>(&ps_acc[(2 * j + 1) * PF_THREADS + tid]), (unsigned int)fix[1] + (unsigned int)fix[3]);
     }
     __syncwarp();
 
@@ -276,7 +296,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
         const int qb = h ? bq1 : bq0;
         const bool ib = h ? inb1 : inb0;
         if (ib) {
-          const uint32_t word = bal_ge[warp * PF_NV + (qb >> 3) * 4 + (qb & 1) + 2 * h];
+          const uint32_t word = bal_gew[warp * PF_NV + (qb >> 3) * 4 + (qb & 1) + 2 * h];
           const bool im = (word >> (g * 4 + ((qb & 7) >> 1))) & 1u;
           const size_t o = (size_t)py * a.W + (h ? px1 : px0);
           a.ids[o] = qb;
@@ -298,32 +318,37 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
         sa[ks][3] = pack2<__half>(xs[2 * ks + 1][2], xs[2 * ks + 1][3]);
       }
       const size_t cs = (size_t)a.H * a.W;
-      float* base0 = a.sem_seg + (size_t)(2 * t4) * cs + (size_t)py * a.W + px0;
+      float* p0 = a.sem_seg + (size_t)(2 * t4) * cs + (size_t)py * a.W + px0;   // class 8 nt + 2 t4
+      float* p1 = p0 + cs;                                                      // class 8 nt + 2 t4 + 1
 #pragma unroll
-      for (int np = 0; np < PF_CP / 16; ++np) {
-        if (np * 16 >= a.ncls) break;
-        float acc[2][4];
+      for (int n3 = 0; n3 < PF_CP / 48; ++n3) {   // 3 x 16 classes at a time: six independent accumulator chains
+        if (n3 * 48 >= a.ncls) break;
+        float acc[6][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int i = 0; i < 6; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 7; ++ks) {
-          uint32_t r[4];
-          pf_ldsm_x4(r, &As[((2 * np + (lane >> 4)) * 8 + (lane & 7)) * PF_ALD + ks * 16 + ((lane >> 3) & 1) * 8]);
-          PfMma<__half>::mma(acc[0], sa[ks], r[0], r[1]);
-          PfMma<__half>::mma(acc[1], sa[ks], r[2], r[3]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            uint32_t r[4];
+            pf_ldsm_x4(r, &As[((2 * (3 * n3 + u) + (lane >> 4)) * 8 + (lane & 7)) * PF_ALD + ks * 16 + ((lane >> 3) & 1) * 8]);
+            PfMma<__half>::mma(acc[2 * u], sa[ks], r[0], r[1]);
+            PfMma<__half>::mma(acc[2 * u + 1], sa[ks], r[2], r[3]);
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = (2 * np + i) * 8 + 2 * t4;
-          float* p = base0 + (size_t)((2 * np + i) * 8) * cs;
+        for (int i = 0; i < 6; ++i) {
+          const int c0 = (6 * n3 + i) * 8 + 2 * t4;
           if (c0 < a.ncls) {
-            if (inb0) p[0] = acc[i][0];
-            if (inb1) p[8] = acc[i][2];
+            if (inb0) p0[0] = acc[i][0];
+            if (inb1) p0[8] = acc[i][2];
           }
           if (c0 + 1 < a.ncls) {
-            if (inb0) p[cs] = acc[i][1];
-            if (inb1) p[cs + 8] = acc[i][3];
+            if (inb0) p1[0] = acc[i][1];
+            if (inb1) p1[8] = acc[i][3];
           }
+          p0 += 8 * cs;
+          p1 += 8 * cs;
         }
       }
     }
@@ -336,8 +361,9 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
       int c = 0, cg = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
+        const uint32_t* bg = zflag[w] ? bal_ge : bal_pos;
         c += __popc(bal_pos[w * PF_NV + vi] & m) + __popc(bal_pos[w * PF_NV + vi + 2] & m);
-        cg += __popc(bal_ge[w * PF_NV + vi] & m) + __popc(bal_ge[w * PF_NV + vi + 2] & m);
+        cg += __popc(bg[w * PF_NV + vi] & m) + __popc(bg[w * PF_NV + vi + 2] & m);
       }
       cnt_tot += c;
       ge_tot += cg;
@@ -347,29 +373,39 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
     if (inst) {
       const int r = lane >> 2, xo = (lane & 3) * 4;        // tile row, x offset of the run
       const int yy = cur.ty0 + r, xx = cur.tx0 + xo;
-      const int hh = xo >> 3, g0 = xo & 7;
       if (yy < a.H && xx < a.W) {
+        const uint32_t* brow = bal_pos + r * PF_NV + 2 * (xo >> 3);   // ballots of the warp that owns row r
+        const int sh0 = (xo & 7) * 4;
         const bool vec = (xx + 3 < a.W) && ((a.W & 3) == 0);
-        for (int k = warp; k < a.K; k += 8) {
-          const int q = k < PF_KMAX ? slots[k] : a.slot_query[k];
-          if (q < 0) continue;
-          const uint32_t word = bal_pos[r * PF_NV + (q >> 3) * 4 + (q & 1) + 2 * hh];
-          const uint32_t b = word >> (g0 * 4 + ((q & 7) >> 1));
-          float* dst = a.inst_masks + ((size_t)k * a.H + yy) * a.W + xx;
-          const float f0 = (b & 1u) ? 1.f : 0.f, f1 = (b & 0x10u) ? 1.f : 0.f;
-          const float f2 = (b & 0x100u) ? 1.f : 0.f, f3 = (b & 0x1000u) ? 1.f : 0.f;
-          if (vec) {
-            *reinterpret_cast<float4*>(dst) = make_float4(f0, f1, f2, f3);
-          } else {
-            dst[0] = f0;
-            if (xx + 1 < a.W) dst[1] = f1;
-            if (xx + 2 < a.W) dst[2] = f2;
-            if (xx + 3 < a.W) dst[3] = f3;
+        const size_t cs = (size_t)a.H * a.W;
+        float* dst = a.inst_masks + (size_t)warp * cs + (size_t)yy * a.W + xx;
+        for (int k = warp; k < a.K; k += 32, dst += 32 * cs) {   // 4 slots in flight
+          int info[4];
+          uint32_t wd[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) info[u] = (k + 8 * u < a.K) ? slots[k + 8 * u] : -1;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) wd[u] = brow[info[u] < 0 ? 0 : (info[u] & 0xff)];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (info[u] < 0) continue;
+            const uint32_t b = wd[u] >> (sh0 + (info[u] >> 8));
+            // bit -> 0.0f / 1.0f: (bit at position p) * (0x3f800000 >> p)
+            const float f0 = __uint_as_float((b & 0x1u) * 0x3f800000u), f1 = __uint_as_float((b & 0x10u) * 0x03f80000u);
+            const float f2 = __uint_as_float((b & 0x100u) * 0x003f8000u), f3 = __uint_as_float((b & 0x1000u) * 0x0003f800u);
+            float* d = dst + (size_t)(8 * u) * cs;
+            if (vec) {
+              *reinterpret_cast<float4*>(d) = make_float4(f0, f1, f2, f3);
+            } else {
+              d[0] = f0;
+              if (xx + 1 < a.W) d[1] = f1;
+              if (xx + 2 < a.W) d[2] = f2;
+              if (xx + 3 < a.W) d[3] = f3;
+            }
           }
         }
       }
     }
-    __syncthreads();   // srcs / ballots may be overwritten by the next tile
   }
 
   // ---- per-CTA partial statistics
@@ -379,8 +415,9 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
     // sum(sigmoid * [x > 0]): slot 2 (q >> 3) + (q & 1) of the 64 threads with t4 == (q & 7) >> 1
     unsigned long long tot = 0;
     const int slot = 2 * (q >> 3) + (q & 1), tq = (q & 7) >> 1;
+    const unsigned int carry = (unsigned int)it << 31;   // it adds of 2^31 per slot (mod 2^32)
     for (int w = 0; w < 8; ++w)
-      for (int gg = 0; gg < 8; ++gg) tot += (unsigned int)ps_acc[slot * PF_THREADS + w * 32 + gg * 4 + tq];
+      for (int gg = 0; gg < 8; ++gg) tot += (unsigned int)ps_acc[slot * PF_THREADS + w * 32 + gg * 4 + tq] - carry;
     float* part = a.partials + ((size_t)blockIdx.x * Q + q) * 5;
     part[0] = (float)cnt_tot;
     part[1] = (float)((double)tot * (1.0 / 4194304.0));
@@ -391,7 +428,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) postproc_fast_kernel(PostprocFa
 }
 
 constexpr size_t pf_smem_bytes(size_t tsize) {
-  return sizeof(__half) * PF_CP * PF_ALD + tsize * PF_QP * PF_SLD + sizeof(uint32_t) * 2 * 8 * PF_NV +
+  return sizeof(__half) * PF_CP * PF_ALD + tsize * 2 * PF_QP * PF_SLD + sizeof(uint32_t) * 2 * 8 * PF_NV + sizeof(int) * 8 +
          sizeof(int) * 28 * PF_THREADS + sizeof(float) * 2 * PF_QP + sizeof(int) * 2 * PF_QP + sizeof(int) * PF_KMAX;
 }
 
@@ -411,7 +448,7 @@ int postproc_fast_ctas(int H, int W);
 bool postproc_fast_ok(int Q, int H4, int W4, int H, int W, int ncls, int K, int dtype) {
   if (dtype != PSALM_F16 && dtype != PSALM_BF16) return false;
   if (Q <= 0 || Q > PF_QP || ncls > PF_CP || H4 <= 0 || W4 <= 0) return false;
-  if (H % H4 || W % W4) return false;
+  if (H % H4 || W % W4 || (W4 & 1) || K > PF_KMAX) return false;   // (even rows: 4-byte aligned source pieces)
   const int fy = H / H4, fx = W / W4;
   auto pow2 = [](int v) { return v >= 1 && v <= 8 && (v & (v - 1)) == 0; };
   if (!pow2(fy) || !pow2(fx)) return false;
@@ -428,10 +465,9 @@ bool postproc_fast_ok(int Q, int H4, int W4, int H, int W, int ncls, int K, int 
     const int xl = (tx0 + PF_TW < W ? tx0 + PF_TW : W) - 1;
     int s1 = (int)pf_srcf(sw, xl) + 1;
     if (s1 > W4 - 1) s1 = W4 - 1;
-    const int n = s1 - (int)pf_srcf(sw, tx0) + 1;
+    const int n = s1 - ((int)pf_srcf(sw, tx0) & ~1) + 1;
     SC = n > SC ? n : SC;
   }
-  (void)K;
   const int tiles = ((W + PF_TW - 1) / PF_TW) * ((H + PF_TH - 1) / PF_TH);
   const int ctas = postproc_fast_ctas(H, W);
   if ((tiles + ctas - 1) / ctas > 255) return false;   // 32-bit fixed-point accumulators

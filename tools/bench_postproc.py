@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--ncu", action="store_true", help="one tensor-core panoptic call between cudaProfilerStart/Stop")
     a = ap.parse_args()
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[a.dtype]
     Q, ncls, H4, W4, H, W = 100, 133, 256, 256, 1024, 1024
@@ -29,6 +30,15 @@ def main():
     negq = (keep.float() - 1).cuda()
     slots = torch.arange(100, dtype=torch.int32).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if a.ncu:
+        _lib.check(_lib.lib().psalm_set_postproc_impl(2), "set")
+        kernels.postproc_fused(logits, H, W, probsT=probsT, wq=wq, negq=negq, slot_query=slots, ncls=ncls)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        kernels.postproc_fused(logits, H, W, probsT=probsT, wq=wq, negq=negq, slot_query=slots, ncls=ncls)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     for impl, name in ((1, "generic"), (2, "tensor-core")):
         _lib.check(_lib.lib().psalm_set_postproc_impl(impl), "set")
         for combo, kw in (("panoptic(sem+inst+pan)", dict(probsT=probsT, wq=wq, negq=negq, slot_query=slots, ncls=ncls)),
