@@ -103,7 +103,10 @@ int psalm_set_attention_impl(int impl);
 /* Causal prefill attention of the LLM (third-party PhiAttention eager path; call site
  * language_model/llava_phi.py:1354-1363).  qkv [B,T,3,nh,hd] with rotary already applied
  * (psalm_rotary_inplace); key_valid [B,T] uint8 (attention_mask) or NULL; out [B,T,nh*hd].
- * fp32 softmax as in the reference. */
+ * fp32 softmax as in the reference.  16-bit storage, head_dim 64, 256 <= T <= 2048: tcgen05 + TMEM kernel
+ * (128-query tiles, S and O accumulators in tensor memory); otherwise the mma.sync flash kernel; fp32
+ * storage: SIMT kernel.  psalm_set_causal_impl: 0 = auto, 1 = mma.sync, 2 = tcgen05 (error if unsupported). */
+int psalm_set_causal_impl(int impl);
 int psalm_causal_attention(const void* qkv, const uint8_t* key_valid, void* out, int B, int T, int nh,
                            int hd, int dtype, void* stream);
 

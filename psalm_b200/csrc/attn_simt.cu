@@ -328,6 +328,9 @@ int mma_cross_attention(const void*, const void*, const void*, const uint32_t*, 
 int mma_window_attention(const void*, const void*, const float*, void*, int, int, int, int, int, int, int,
                          cudaStream_t);
 extern int g_splitk_mode;
+bool tc5_causal_ok(int B, int T_, int nh, int hd, int dtype);
+int tc5_causal_attention(const void*, const uint8_t*, void*, int, int, int, int, int, cudaStream_t);
+static int g_causal_impl = 0;   // 0 auto, 1 mma.sync, 2 tcgen05
 static int g_attn_impl = 0;  // 0 = auto (tensor cores for 16-bit storage), 1 = force the fp32 SIMT kernels
 }  // namespace psalm
 
@@ -337,6 +340,12 @@ extern "C" int psalm_set_attention_impl(int impl) {
   PSALM_REQUIRE(impl >= 0 && impl <= 3, "set_attention_impl: 0 (auto), 1 (simt), 2 (split-K via workspace) or 3 (split-K via cluster)");
   g_attn_impl = impl == 1 ? 1 : 0;
   g_splitk_mode = impl == 2 ? 1 : (impl == 3 ? 2 : 0);
+  return PSALM_OK;
+}
+
+extern "C" int psalm_set_causal_impl(int impl) {
+  PSALM_REQUIRE(impl >= 0 && impl <= 2, "set_causal_impl: 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+  g_causal_impl = impl;
   return PSALM_OK;
 }
 
@@ -370,6 +379,11 @@ extern "C" int psalm_window_attention(const void* qkv, const void* qkv_bias, con
 extern "C" int psalm_causal_attention(const void* qkv, const uint8_t* key_valid, void* out, int B, int T_,
                                       int nh, int hd, int dtype, void* stream) {
   PSALM_REQUIRE(qkv && out, "causal_attention: null pointer");
+  if (g_attn_impl == 0 && g_causal_impl == 2)
+    return tc5_causal_attention(qkv, key_valid, out, B, T_, nh, hd, dtype, (cudaStream_t)stream);
+  // tcgen05 kernel: 128-query tiles; below ~2 tiles per head the 64-row mma.sync kernel fills the GPU better
+  if (g_attn_impl == 0 && g_causal_impl == 0 && T_ >= 256 && tc5_causal_ok(B, T_, nh, hd, dtype))
+    return tc5_causal_attention(qkv, key_valid, out, B, T_, nh, hd, dtype, (cudaStream_t)stream);
   if (dtype != PSALM_F32 && g_attn_impl == 0 && (hd == 32 || hd == 64))
     return mma_causal_attention(qkv, key_valid, out, B, T_, nh, hd, dtype, (cudaStream_t)stream);
   AttnDims dm{B, nh, T_, T_, 1, 1.0f / sqrtf((float)hd)};

@@ -177,3 +177,34 @@ def test_mask_projection_tcgen05(dt, B, Q, P, attn_impl):
     finally:
         _lib.lib().psalm_set_mask_proj_impl(0)
     _close(out, ref, dt)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("T,padded", [(64, False), (130, True), (257, False), (900, True), (1100, False), (1100, True), (2048, False)])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_causal_attention_impls(dt, T, padded, impl):
+    """mma.sync flash kernel (1) and tcgen05 + TMEM kernel (2) against the fp32 restatement."""
+    from psalm_b200 import _lib
+    torch.manual_seed(T + impl)
+    B, nh, hd = 2, 3, 64
+    qkv = torch.randn(B, T, 3, nh, hd).to(DT[dt])
+    kv = None
+    if padded:
+        kv = torch.ones(B, T, dtype=torch.uint8)
+        kv[1, T - 9:] = 0
+        kv[0, 5:40] = 0          # a hole inside the sequence
+        kv[1, 0] = 0             # first key invalid: row 0 of batch 1 has no valid key at all
+    ref = emu.causal_attention(qkv.float(), kv, B, T, nh, hd)
+    try:
+        _lib.check(_lib.lib().psalm_set_causal_impl(impl), "set_causal_impl")
+        out = kernels.causal_attention(qkv.cuda(), kv.cuda() if kv is not None else None, B, T, nh, hd)
+        out2 = kernels.causal_attention(qkv.cuda(), kv.cuda() if kv is not None else None, B, T, nh, hd)
+    finally:
+        _lib.lib().psalm_set_causal_impl(0)
+    assert torch.equal(out, out2)
+    valid = torch.ones(B, T, dtype=torch.bool) if kv is None else kv.bool()
+    if kv is not None:
+        valid[1, 0] = False      # fully-masked query row: implementation-defined (zeros here, NaN in torch)
+    o, r = out.float().cpu()[valid], ref[valid]
+    err = (o - r).abs().max() / (r.abs().max() + 1e-30)
+    assert err < TOL[dt], "rel-to-max error %.3e" % err
