@@ -312,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B = 1 from the committed
                          # `ncu --set full` capture (profiles/r1i_msda_fused_bf16_ncu_details.txt): 23.43 MB read +
                          # 0.01 MB written inside the capture window (the 11 MB output stays in the 126 MB L2)
-                         "traffic": 23439104 * B if args.dtype != "f32" else None,
+                         "traffic": 23432192 * B if args.dtype != "f32" else None,
                          "traffic_source": "ncu capture committed under profiles/ (not measured in this run)",
                          "peak_source": peak_src,
                          "avg_us": avg_us, "launches_timed": len(msda_us), "algorithmic_bytes_per_launch": alg,
