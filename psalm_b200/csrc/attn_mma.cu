@@ -497,6 +497,9 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     if (ox >= Wp) ox -= Wp;
     tok[tid] = (oy < H && ox < W) ? (bi * H + oy) * W + ox : -1;
   }
+  // the -100 shift mask only exists in windows of the last window row / column (they hold several regions)
+  const int win_ = z % nW;
+  const bool wmask = shift > 0 && (win_ / nWx == nW / nWx - 1 || win_ % nWx == nWx - 1);
   __syncthreads();
   auto prefetch = [&](int h, int stage) {
     T* dst0 = bufs + (size_t)stage * 3 * N * LD;
@@ -550,23 +553,35 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     const float* rel0 = rel + ((size_t)h * N + r0) * N;
     const float* rel1 = rel + ((size_t)h * N + r1) * N;
     float mx[2] = {-INFINITY, -INFINITY};
+    const float scl = sc * kLog2e;   // scores go straight to the log2 domain: s * scale * log2e + bias * log2e
+    if (!wmask) {                    // window does not touch the wrapped border: no shift mask (warp-uniform)
 #pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-      const int kj = nt * 8 + 2 * t4;
-      const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
-      const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
-      float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
-      if (shift > 0) {
-        const int ra = reg[kj], rb = reg[kj + 1];
-        m00 = ra != reg0 ? -100.f : 0.f; m01 = rb != reg0 ? -100.f : 0.f;
-        m10 = ra != reg1 ? -100.f : 0.f; m11 = rb != reg1 ? -100.f : 0.f;
+      for (int nt = 0; nt < 18; ++nt) {
+        const int kj = nt * 8 + 2 * t4;
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
+        const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
+        s[nt][0] = fmaf(s[nt][0], scl, b0.x * kLog2e);
+        s[nt][1] = fmaf(s[nt][1], scl, b0.y * kLog2e);
+        s[nt][2] = fmaf(s[nt][2], scl, b1.x * kLog2e);
+        s[nt][3] = fmaf(s[nt][3], scl, b1.y * kLog2e);
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
       }
-      s[nt][0] = (fmaf(s[nt][0], sc, b0.x) + m00) * kLog2e;
-      s[nt][1] = (fmaf(s[nt][1], sc, b0.y) + m01) * kLog2e;
-      s[nt][2] = (fmaf(s[nt][2], sc, b1.x) + m10) * kLog2e;
-      s[nt][3] = (fmaf(s[nt][3], sc, b1.y) + m11) * kLog2e;
-      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    } else {
+      constexpr float kNeg = -100.f * kLog2e;   // the reference's additive -100 (swin_trans.py:232-240)
+#pragma unroll
+      for (int nt = 0; nt < 18; ++nt) {
+        const int kj = nt * 8 + 2 * t4;
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
+        const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
+        const int ra = reg[kj], rb = reg[kj + 1];
+        s[nt][0] = fmaf(s[nt][0], scl, b0.x * kLog2e) + (ra != reg0 ? kNeg : 0.f);
+        s[nt][1] = fmaf(s[nt][1], scl, b0.y * kLog2e) + (rb != reg0 ? kNeg : 0.f);
+        s[nt][2] = fmaf(s[nt][2], scl, b1.x * kLog2e) + (ra != reg1 ? kNeg : 0.f);
+        s[nt][3] = fmaf(s[nt][3], scl, b1.y * kLog2e) + (rb != reg1 ? kNeg : 0.f);
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+      }
     }
     float sum[2] = {0.f, 0.f};
 #pragma unroll

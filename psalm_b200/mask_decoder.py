@@ -36,8 +36,6 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
                 for j, n in enumerate("qkv"):
                     w["%s%d.%s.w" % (tag, i, n)] = cv(W[j * H:(j + 1) * H])
                     w["%s%d.%s.b" % (tag, i, n)] = cv(b[j * H:(j + 1) * H])
-                if tag == "s":  # q and k share the input (tgt + query_pos): one GEMM
-                    w["s%d.qk.w" % i], w["s%d.qk.b" % i] = cv(W[:2 * H]), cv(b[:2 * H])
                 w["%s%d.o.w" % (tag, i)], w["%s%d.o.b" % (tag, i)] = cv(g(p + attn + ".out_proj.weight")), cv(g(p + attn + ".out_proj.bias"))
                 w["%s%d.n.w" % (tag, i)], w["%s%d.n.b" % (tag, i)] = cv(g(p + "norm.weight")), cv(g(p + "norm.bias"))
             p = "transformer_ffn_layers.%d." % i
@@ -117,9 +115,11 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             output = kernels.add_layer_norm(output, w["x%d.n.w" % i], w["x%d.n.b" % i],
                                             r1=F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]))
             # query self-attention (:35-45): q = k = tgt + query_pos, v = tgt
-            qk = F.linear(output + qpos, w["s%d.qk.w" % i], w["s%d.qk.b" % i])
+            xq = output + qpos
+            q = F.linear(xq, w["s%d.q.w" % i], w["s%d.q.b" % i])     # three contiguous outputs: no slicing copies
+            k = F.linear(xq, w["s%d.k.w" % i], w["s%d.k.b" % i])
             v = F.linear(output, w["s%d.v.w" % i], w["s%d.v.b" % i])
-            a = kernels.cross_attention(qk[..., :Hd].contiguous(), qk[..., Hd:].contiguous(), v, None, None, nh, splits=1)
+            a = kernels.cross_attention(q, k, v, None, None, nh, splits=1)
             output = kernels.add_layer_norm(output, w["s%d.n.w" % i], w["s%d.n.b" % i],
                                             r1=F.linear(a, w["s%d.o.w" % i], w["s%d.o.b" % i]))
             # FFN (:158-162)
