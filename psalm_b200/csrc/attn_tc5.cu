@@ -14,7 +14,8 @@
 //                  numerator and denominator share the reference), and only then is the O row rescaled in TMEM
 //                  (tcgen05.ld / st) - after the first tile that is rare, so there is no per-tile O traffic.
 // K is double-buffered with cp.async one full tile ahead, V is refilled as soon as the previous PV MMA has
-// retired; the second CTA on the SM covers what is left of the tensor-core / softmax bubbles.  fp32 accumulation.
+// retired; the S and PV MMAs are issued from two different warps so that no single softmax warp carries both issue
+// latencies; the second CTA on the SM covers what is left of the tensor-core / softmax bubbles.  fp32 accumulation.
 #include <type_traits>
 
 #include "common.cuh"
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(128, 2) causal_tc5_kernel(const T* __restrict_
   asm volatile("cp.async.wait_group 2;\n" ::);
   asm volatile("fence.proxy.async.shared::cta;\n" ::);
   __syncthreads();
-  if (tid == 0) issue_s(0);
+  if (tid == 32) issue_s(0);
 
   const int row = tid, qi = q0 + row;
   float m_ref = -INFINITY, l_run = 0.f;   // reference maximum (log2 domain) of P and of the row sum
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(128, 2) causal_tc5_kernel(const T* __restrict_
     asm volatile("fence.proxy.async.shared::cta;\n" ::);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
     __syncthreads();
-    if (tid == 0 && t + 1 < ntiles) issue_s(t + 1);
+    if (tid == 32 && t + 1 < ntiles) issue_s(t + 1);   // warp 1 pays the S issue latency, warp 2 the PV one
 
     // ---- softmax of row `row` over the 128 keys of this tile (scores in the log2 domain)
     const bool diag = (t == qt);
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(128, 2) causal_tc5_kernel(const T* __restrict_
     asm volatile("fence.proxy.async.shared::cta;\n" ::);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 64) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
       const uint32_t a0 = fa_smem_u32(sP), b0 = fa_smem_u32(sV);
 #pragma unroll
