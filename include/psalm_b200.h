@@ -74,7 +74,11 @@ int psalm_msda_forward(const void* value, const int64_t* shapes, const int64_t* 
  *   ow     [B,Lq,M*L*P*3]: per query, first M*L*P*2 offsets (m,l,p,xy order), then M*L*P logits
  *          dtype ow_dtype (F32 / F16 / BF16).  Lq must equal S (encoder self-attention).
  *   out    [B,Lq,M*D] dtype value_dtype
- *   shapes_host/starts_host: HOST int64 arrays. */
+ *   shapes_host/starts_host: HOST int64 arrays.
+ * Two lane mappings: one lane group per (query, head) (default, measured faster) and paired columns (2*D/8 lanes
+ * per (query, head), the two x-adjacent bilinear corners are one contiguous access).  psalm_set_msda_impl:
+ * 0 = auto, 1 = single group, 2 = paired columns. */
+int psalm_set_msda_impl(int impl);
 int psalm_msda_encoder_fused(const void* value, const void* ow, void* out,
                              const int64_t* shapes_host, const int64_t* starts_host,
                              int B, int S, int M, int D, int L, int P,

@@ -97,11 +97,14 @@ def _fused_inputs(shapes, B, M, D, L, P, seed):
 
 
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
-def test_fused_encoder_kernel(dt):
+@pytest.mark.parametrize("impl", [1, 2], ids=["single-group", "paired-columns"])
+@pytest.mark.parametrize("shapes", [[(6, 9), (12, 18), (24, 36)], [(5, 7), (11, 13), (21, 27)]], ids=["even", "odd"])
+def test_fused_encoder_kernel(dt, impl, shapes):
     """softmax + reference points + location arithmetic fused in-kernel equals the unfused module
-    arithmetic (ops/modules/ms_deform_attn.py:103-110 + get_reference_points, msdeformattn.py:76-87)."""
+    arithmetic (ops/modules/ms_deform_attn.py:103-110 + get_reference_points, msdeformattn.py:76-87);
+    both lane mappings of the kernel, even and odd map widths (ragged tiles, unaligned column pairs)."""
     from oracle import psalm_oracle as O
-    shapes = [(6, 9), (12, 18), (24, 36)]
+    from psalm_b200 import _lib
     B, M, D, L, P = 2, 8, 32, 3, 4
     value, off, logit = _fused_inputs(shapes, B, M, D, L, P, 1)
     S = value.shape[1]
@@ -111,8 +114,12 @@ def test_fused_encoder_kernel(dt):
     lgq = torch.from_numpy(logit).to(tdt)
     ow = torch.cat([offq.reshape(B, S, -1), lgq.reshape(B, S, -1)], -1).contiguous().cuda()
     v_hm = vq.permute(0, 2, 1, 3).contiguous().cuda()
-    out = msda.msda_encoder_fused(v_hm, ow, shapes, _starts(shapes), P)
-    torch.cuda.synchronize()
+    try:
+        _lib.check(_lib.lib().psalm_set_msda_impl(impl), "set_msda_impl")
+        out = msda.msda_encoder_fused(v_hm, ow, shapes, _starts(shapes), P)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().psalm_set_msda_impl(0)
     ref_pts = O.encoder_reference_points(shapes, B).double()
     normalizer = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float64)
     loc = ref_pts[:, :, None, :, None, :] + offq.double() / normalizer[None, None, None, :, None, :]
