@@ -162,8 +162,10 @@ int psalm_add_layernorm(const void* x, const void* r1, const void* r2, const voi
 
 /* GroupNorm (+ optional ReLU) of a token-major map x [B,N,C] (statistics over N x C/groups per group),
  * msdeformattn.py:199-203,244-252.  Deterministic (no atomics).
+ * pre_bias [C] or NULL: per-channel bias of the conv / Linear that produced x, added before the statistics
+ * (GroupNorm(x + pre_bias)): the producer runs without its separate broadcast bias-add pass.
  * stats_workspace: at least 8 * B * groups * (1 + ceil(N / 256)) bytes. */
-int psalm_groupnorm_tokens(const void* x, const void* weight, const void* bias, void* y,
+int psalm_groupnorm_tokens(const void* x, const void* pre_bias, const void* weight, const void* bias, void* y,
                            double* stats_workspace, int B, int N, int C, int groups, float eps, int relu,
                            int dtype, void* stream);
 

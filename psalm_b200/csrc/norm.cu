@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(128) add_layernorm_kernel(const T* __restrict_
 // in a fixed order in double and emits (mean, rstd); (3) streaming apply.
 // C <= 1024, C % (4*groups) == 0, 256 % (C/4) == 0.
 template <typename T>
-__global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restrict__ x, float2* __restrict__ part,
+__global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias,
+                                                                float2* __restrict__ part,
                                                                 int N, int C, int groups, int tokens_per_cta) {
   __shared__ float ts[256], tq[256];
   const int b = blockIdx.y;
@@ -118,11 +119,14 @@ __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restr
   const int cidx = threadIdx.x % chunks, trow = threadIdx.x / chunks;
   float s = 0.f, q = 0.f;
   if (trow < tpb) {
+    float pb[4] = {0.f, 0.f, 0.f, 0.f};        // per-channel bias of the producing conv / linear, folded in here
+    if (pre_bias) load4<T>(pre_bias + cidx * 4, pb);
     for (int t = t0 + trow; t < t1; t += tpb) {
       float f[4];
       load4<T>(x + ((size_t)b * N + t) * C + cidx * 4, f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        f[i] += pb[i];
         s += f[i];
         q = fmaf(f[i], f[i], q);
       }
@@ -162,7 +166,8 @@ __global__ void groupnorm_finalize_kernel(const float2* __restrict__ part, float
 }
 
 template <typename T>
-__global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __restrict__ mean_rstd,
+__global__ void groupnorm_apply_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias,
+                                       const float2* __restrict__ mean_rstd,
                                        const T* __restrict__ w, const T* __restrict__ bias, T* __restrict__ y,
                                        int B, int N, int C, int groups, int relu) {
   const int cpg = C / groups;
@@ -172,13 +177,14 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __
     const int c = (int)(e % C);
     const int b = (int)(e / ((long long)N * C));
     const float2 mr = mean_rstd[(size_t)b * groups + c / cpg];
-    float f[4], gw[4], gb[4], o[4];
+    float f[4], gw[4], gb[4], o[4], pb[4] = {0.f, 0.f, 0.f, 0.f};
     load4<T>(x + e, f);
     load4<T>(w + c, gw);
     load4<T>(bias + c, gb);
+    if (pre_bias) load4<T>(pre_bias + c, pb);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      o[k] = (f[k] - mr.x) * mr.y * gw[k] + gb[k];
+      o[k] = (f[k] + pb[k] - mr.x) * mr.y * gw[k] + gb[k];
       if (relu) o[k] = fmaxf(o[k], 0.f);
     }
     store4<T>(y + e, o);
@@ -205,20 +211,20 @@ static int launch_ln(const void* x, const void* r1, const void* r2, const void* 
 }
 
 template <typename T>
-static int launch_gn(const void* x, const void* w, const void* b, void* y, double* workspace, int B, int N, int C,
+static int launch_gn(const void* x, const void* pre_bias, const void* w, const void* b, void* y, double* workspace, int B, int N, int C,
                      int groups, float eps, int relu, cudaStream_t st) {
   const int tokens_per_cta = 256;
   const int n_part = (N + tokens_per_cta - 1) / tokens_per_cta;
   float2* mean_rstd = reinterpret_cast<float2*>(workspace);                    // [B*groups]
   float2* part = mean_rstd + (size_t)B * groups;                               // [B*groups][n_part]
   dim3 g1(n_part, B);
-  groupnorm_partial_kernel<T><<<g1, 256, 0, st>>>((const T*)x, part, N, C, groups, tokens_per_cta);
+  groupnorm_partial_kernel<T><<<g1, 256, 0, st>>>((const T*)x, (const T*)pre_bias, part, N, C, groups, tokens_per_cta);
   const int n_bg = B * groups;
   groupnorm_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(part, mean_rstd, n_bg, n_part,
                                                               (double)N * (C / groups), eps);
   const long long n4 = (long long)B * N * C / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-  groupnorm_apply_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>((const T*)x, mean_rstd, (const T*)w, (const T*)b,
+  groupnorm_apply_kernel<T><<<blocks > 0 ? blocks : 1, 256, 0, st>>>((const T*)x, (const T*)pre_bias, mean_rstd, (const T*)w, (const T*)b,
                                                                      (T*)y, B, N, C, groups, relu);
   return check_launch("groupnorm_tokens");
 }
@@ -242,7 +248,7 @@ extern "C" int psalm_add_layernorm(const void* x, const void* r1, const void* r2
   return PSALM_E_ARG;
 }
 
-extern "C" int psalm_groupnorm_tokens(const void* x, const void* weight, const void* bias, void* y,
+extern "C" int psalm_groupnorm_tokens(const void* x, const void* pre_bias, const void* weight, const void* bias, void* y,
                                       double* stats_workspace, int B, int N, int C, int groups, float eps,
                                       int relu, int dtype, void* stream) {
   PSALM_REQUIRE(x && weight && bias && y && stats_workspace, "groupnorm_tokens: null pointer");
@@ -250,9 +256,9 @@ extern "C" int psalm_groupnorm_tokens(const void* x, const void* weight, const v
                 "groupnorm_tokens: unsupported C=%d groups=%d", C, groups);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case PSALM_F32: return launch_gn<float>(x, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
-    case PSALM_F16: return launch_gn<__half>(x, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
-    case PSALM_BF16: return launch_gn<__nv_bfloat16>(x, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
+    case PSALM_F32: return launch_gn<float>(x, pre_bias, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
+    case PSALM_F16: return launch_gn<__half>(x, pre_bias, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
+    case PSALM_BF16: return launch_gn<__nv_bfloat16>(x, pre_bias, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
   }
   set_error("groupnorm_tokens: unknown dtype %d", dtype);
   return PSALM_E_ARG;

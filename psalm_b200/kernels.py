@@ -190,14 +190,16 @@ def add_layer_norm(x, weight, bias, eps=1e-5, r1=None, r2=None, return_sum=False
     return (s, y) if return_sum else y
 
 
-def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False):
-    """GroupNorm(groups) (+ReLU) of a token-major map [B,N,C]."""
-    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")):
+def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False, pre_bias=None):
+    """GroupNorm(groups) (+ReLU) of a token-major map [B,N,C]; `pre_bias` [C] = bias of the producing conv / Linear,
+    added inside the kernel (GroupNorm(x + pre_bias))."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")) + (((pre_bias, "pre_bias"),) if pre_bias is not None else ()):
         _chk(t, "group_norm_tokens." + n)
     B, N, C = x.shape
     stats = torch.empty(B * groups * (1 + (N + 255) // 256), dtype=torch.float64, device=x.device)
     y = torch.empty_like(x)
-    rc = _lib.lib().psalm_groupnorm_tokens(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(stats),
+    rc = _lib.lib().psalm_groupnorm_tokens(_lib.ptr(x), _lib.ptr(pre_bias) if pre_bias is not None else None,
+                                           _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(stats),
                                            B, N, C, groups, float(eps), 1 if relu else 0,
                                            _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
     _lib.check(rc, "psalm_groupnorm_tokens")

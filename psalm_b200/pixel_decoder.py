@@ -144,7 +144,8 @@ class MSDeformAttnPixelDecoder:
         Hl, Wl = shapes[-1]
         up = kernels.bilinear_tokens(outs[-1], Hl, Wl, H2, W2)   # fp32 math, rounded to dtype like `.to(x.dtype)`
         y = (cur + up).view(B, H2, W2, cfg.hidden).permute(0, 3, 1, 2)   # channels-last NCHW view
-        y = F.conv2d(y, w["l1.w"], w["l1.b"], padding=1).permute(0, 2, 3, 1).reshape(B, H2 * W2, cfg.hidden)
-        y = kernels.group_norm_tokens(y.contiguous(), w["l1.gw"], w["l1.gb"], relu=True)
+        # the conv runs without its bias (a separate broadcast-add pass in cuDNN); GroupNorm adds it in-kernel
+        y = F.conv2d(y, w["l1.w"], None, padding=1).permute(0, 2, 3, 1).reshape(B, H2 * W2, cfg.hidden)
+        y = kernels.group_norm_tokens(y.contiguous(), w["l1.gw"], w["l1.gb"], relu=True, pre_bias=w["l1.b"])
         mask_features = F.linear(y, w["mf.w"], w["mf.b"])
         return mask_features, outs, shapes

@@ -25,6 +25,7 @@ class SwinTransformer:
         cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
         w = {}
         w["pe.w"] = cv(g("patch_embed.proj.weight")).contiguous(memory_format=torch.channels_last)
+        w["pe.w2"] = cv(g("patch_embed.proj.weight").reshape(g("patch_embed.proj.weight").shape[0], -1))   # [C, 3*ps*ps]
         w["pe.b"] = cv(g("patch_embed.proj.bias"))
         w["pe.nw"], w["pe.nb"] = cv(g("patch_embed.norm.weight")), cv(g("patch_embed.norm.bias"))
         ws = cfg.window
@@ -58,16 +59,27 @@ class SwinTransformer:
     # -- token-major pipeline ----------------------------------------------------------------------
     def forward_tokens(self, images):
         cfg, w = self.cfg, self.w
-        x = images.to(device=self.device, dtype=self.dtype)
-        _, _, H, W = x.shape
+        _, Cin, H, W = images.shape
         ps = cfg.patch
-        if W % ps != 0:  # swin_trans.py:431-434
-            x = F.pad(x, (0, ps - W % ps))
-        if H % ps != 0:
-            x = F.pad(x, (0, 0, 0, ps - H % ps))
-        x = F.conv2d(x.contiguous(memory_format=torch.channels_last), w["pe.w"], w["pe.b"], stride=ps)
-        B, C, Wh, Ww = x.shape
-        x = x.permute(0, 2, 3, 1).reshape(B, Wh * Ww, C)
+        if H % ps == 0 and W % ps == 0:
+            # non-overlapping ps x ps patches: the stride-ps convolution (swin_trans.py:427-441) is a GEMM over
+            # unfolded patches.  One strided copy does the unfold and the cast; bias rides in the GEMM epilogue
+            # (cuDNN's conv would add it in a separate broadcast pass).
+            B, Wh, Ww = images.shape[0], H // ps, W // ps
+            src = images.to(device=self.device).view(B, Cin, Wh, ps, Ww, ps).permute(0, 2, 4, 1, 3, 5)
+            patches = torch.empty((B, Wh, Ww, Cin, ps, ps), dtype=self.dtype, device=self.device)
+            patches.copy_(src)
+            x = F.linear(patches.view(B, Wh * Ww, Cin * ps * ps), w["pe.w2"], w["pe.b"])
+        else:
+            x = images.to(device=self.device, dtype=self.dtype)
+            if W % ps != 0:  # swin_trans.py:431-434
+                x = F.pad(x, (0, ps - W % ps))
+            if H % ps != 0:
+                x = F.pad(x, (0, 0, 0, ps - H % ps))
+            x = F.conv2d(x.contiguous(memory_format=torch.channels_last), w["pe.w"], w["pe.b"], stride=ps)
+            B, C, Wh, Ww = x.shape
+            x = x.permute(0, 2, 3, 1).reshape(B, Wh * Ww, C)
+        C = x.shape[-1]
         x = kernels.add_layer_norm(x.contiguous(), w["pe.nw"], w["pe.nb"])
         outs, sizes = [], []
         ws = cfg.window

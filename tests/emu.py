@@ -118,8 +118,9 @@ def add_layer_norm(x, weight, bias, eps=1e-5, r1=None, r2=None, return_sum=False
     return (s.to(x.dtype), y) if return_sum else y
 
 
-def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False):
-    y = F.group_norm(x.float().transpose(1, 2), groups, weight.float(), bias.float(), eps).transpose(1, 2)
+def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False, pre_bias=None):
+    xf = x.float() if pre_bias is None else x.float() + pre_bias.float()
+    y = F.group_norm(xf.transpose(1, 2), groups, weight.float(), bias.float(), eps).transpose(1, 2)
     if relu:
         y = F.relu(y)
     return y.contiguous().to(x.dtype)

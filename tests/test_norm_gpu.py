@@ -46,6 +46,10 @@ def test_group_norm_tokens(dt, N, C, relu):
     ref = emu.group_norm_tokens(x, w, b, 32, 1e-5, relu)
     out = kernels.group_norm_tokens(x.cuda(), w.cuda(), b.cuda(), 32, 1e-5, relu)
     _close(out, ref, dt)
+    pb = (torch.randn(C) * 2).to(DT[dt])          # bias of the producing conv, folded into the kernel
+    ref = emu.group_norm_tokens(x, w, b, 32, 1e-5, relu, pre_bias=pb)
+    out = kernels.group_norm_tokens(x.cuda(), w.cuda(), b.cuda(), 32, 1e-5, relu, pre_bias=pb.cuda())
+    _close(out, ref, dt)
 
 
 def test_unsupported_width_raises():
