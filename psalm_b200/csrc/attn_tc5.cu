@@ -281,27 +281,34 @@ __global__ void __launch_bounds__(128, 2) causal_tc5_kernel(const T* __restrict_
       }
     }
     float ps[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains
+    // p = 2^(s * scale - m_ref), packed to 16 bits and written as the A operand of the PV MMA: 32 keys = 4 chunks
+    // of 16 B in key block (w >> 1), chunks (w & 1) * 4 .. + 3 of this row.  Two real code paths (the mask
+    // tests would otherwise be executed as selects on every tile: +25 % instructions).
+    auto emit = [&](auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const uint32_t bm = masked ? blk[w] : 0u;
-      uint32_t pk[16];
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t bm = kMasked ? blk[w] : 0u;
+        uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float p0 = fa_exp2(fmaf(__uint_as_float(v[w * 32 + j]), scale_log2e, -msub));
-        float p1 = fa_exp2(fmaf(__uint_as_float(v[w * 32 + j + 1]), scale_log2e, -msub));
-        if (masked) {
-          p0 = ((bm >> j) & 1u) ? 0.f : p0;
-          p1 = ((bm >> (j + 1)) & 1u) ? 0.f : p1;
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = fa_exp2(fmaf(__uint_as_float(v[w * 32 + j]), scale_log2e, -msub));
+          float p1 = fa_exp2(fmaf(__uint_as_float(v[w * 32 + j + 1]), scale_log2e, -msub));
+          if (kMasked) {
+            p0 = ((bm >> j) & 1u) ? 0.f : p0;
+            p1 = ((bm >> (j + 1)) & 1u) ? 0.f : p1;
+          }
+          ps[(j >> 1) & 3] += p0 + p1;
+          pk[j >> 1] = pack2<T>(p0, p1);
         }
-        ps[(j >> 1) & 3] += p0 + p1;
-        pk[j >> 1] = pack2<T>(p0, p1);
-      }
-      // 32 keys = 4 chunks of 16 B: key block (w >> 1), chunks (w & 1) * 4 .. + 3 of this row
-      unsigned char* prow = sP + (w >> 1) * FA_TILE;
+        unsigned char* prow = sP + (w >> 1) * FA_TILE;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(prow + fa_swz(row, (w & 1) * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-    }
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(prow + fa_swz(row, (w & 1) * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+    };
+    if (masked) emit(std::true_type{});
+    else emit(std::false_type{});
     l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
 
     // ---- V(t) landed, P written: O += P V
