@@ -92,6 +92,9 @@ int psalm_msda_encoder_fused(const void* value, const void* ow, void* out,
  *   qkv      [B, H*W, 3*C]  output of the qkv Linear on norm1(x), UNPADDED and UNSHIFTED token order
  *   qkv_bias [3*C]          value of a zero-padded token after the Linear (swin_trans.py:207-214)
  *   rel_bias [nh, ws*ws, ws*ws] fp32, relative_position_bias_table gathered by relative_position_index
+ *            (swin_trans.py:98-114, 137-141).  It MUST be such a gather, i.e. entry (i, j) depends only on the
+ *            relative offset of tokens i and j: the tensor-core kernel reads the (2 ws - 1)^2 distinct values of
+ *            each head once into shared memory instead of streaming the dense table (83 KB per window-head).
  *   out      [B, H*W, C]    attention output before `proj`, original token order (padding cropped)
  * ------------------------------------------------------------------------------------------ */
 int psalm_window_attention(const void* qkv, const void* qkv_bias, const float* rel_bias, void* out,

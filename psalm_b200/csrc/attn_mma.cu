@@ -480,7 +480,14 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
   extern __shared__ __align__(16) unsigned char win_smem[];
   T* bufs = reinterpret_cast<T*>(win_smem);                     // [2 stages][3: q,k,v][N * LD]
   int* tok = reinterpret_cast<int*>(bufs + 2 * 3 * N * LD);     // [N]
-  unsigned char* reg = reinterpret_cast<unsigned char*>(tok + N);
+  unsigned char* reg = reinterpret_cast<unsigned char*>(tok + N);  // [N]
+  // The relative-position bias of a head has only (2 WS - 1)^2 = 529 distinct values (swin_trans.py:98-114 gathers
+  // them into the dense [N, N] table); reading the dense table costs 83 KB of L2 traffic per (window, head) - 11x
+  // the q/k/v bytes.  The 529 values are picked out of the dense table once per head into shared memory
+  // (pre-multiplied by log2e) and indexed with (row base + column offset).
+  constexpr int NREL = (2 * WS - 1) * (2 * WS - 1);
+  float* relc = reinterpret_cast<float*>(reg + N);               // [2 stages][NREL + 3]
+  short* coff = reinterpret_cast<short*>(relc + 2 * (NREL + 3)); // [N] column part of the compact index
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int z = blockIdx.x, h0 = blockIdx.y * HPC;
@@ -496,6 +503,7 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     if (oy >= Hp) oy -= Hp;
     if (ox >= Wp) ox -= Wp;
     tok[tid] = (oy < H && ox < W) ? (bi * H + oy) * W + ox : -1;
+    coff[tid] = (short)(-(i * (2 * WS - 1) + j));
   }
   // the -100 shift mask only exists in windows of the last window row / column (they hold several regions)
   const int win_ = z % nW;
@@ -514,9 +522,19 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     }
     cp_async_commit();
   };
+  auto load_rel = [&](int h, int stage) {   // compact bias table of head h: entry (dy, dx) from dense[(i, j)] with i - j = (dy, dx)
+    for (int c = tid; c < NREL; c += 288) {
+      const int dy = c / (2 * WS - 1) - (WS - 1), dx = c % (2 * WS - 1) - (WS - 1);
+      const int i = max(dy, 0) * WS + max(dx, 0), j = max(-dy, 0) * WS + max(-dx, 0);
+      relc[stage * (NREL + 3) + c] = __ldg(rel + ((size_t)h * N + i) * N + j) * kLog2e;
+    }
+  };
   prefetch(h0, 0);
+  load_rel(h0, 0);
   const float sc = rsqrtf((float)HD);
   const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const int rb0 = (r0 / WS + WS - 1) * (2 * WS - 1) + (r0 % WS) + WS - 1;   // row part of the compact bias index
+  const int rb1 = (r1 / WS + WS - 1) * (2 * WS - 1) + (r1 % WS) + WS - 1;
   const int reg0 = reg[r0], reg1 = reg[r1];
   const int tk0 = tok[r0], tk1 = tok[r1];
 #pragma unroll 1
@@ -524,6 +542,7 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     const int h = h0 + hi, stage = hi & 1;
     if (hi + 1 < HPC) {
       prefetch(h + 1, stage ^ 1);
+      load_rel(h + 1, stage ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -550,20 +569,20 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
         mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
       }
     }
-    const float* rel0 = rel + ((size_t)h * N + r0) * N;
-    const float* rel1 = rel + ((size_t)h * N + r1) * N;
+    const float* rc0 = relc + stage * (NREL + 3) + rb0;
+    const float* rc1 = relc + stage * (NREL + 3) + rb1;
     float mx[2] = {-INFINITY, -INFINITY};
     const float scl = sc * kLog2e;   // scores go straight to the log2 domain: s * scale * log2e + bias * log2e
     if (!wmask) {                    // window does not touch the wrapped border: no shift mask (warp-uniform)
 #pragma unroll
       for (int nt = 0; nt < 18; ++nt) {
         const int kj = nt * 8 + 2 * t4;
-        const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
-        const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
-        s[nt][0] = fmaf(s[nt][0], scl, b0.x * kLog2e);
-        s[nt][1] = fmaf(s[nt][1], scl, b0.y * kLog2e);
-        s[nt][2] = fmaf(s[nt][2], scl, b1.x * kLog2e);
-        s[nt][3] = fmaf(s[nt][3], scl, b1.y * kLog2e);
+        const int c2 = *reinterpret_cast<const int*>(&coff[kj]);   // column offsets of keys kj, kj + 1
+        const int ca = (short)(c2 & 0xffff), cb = c2 >> 16;
+        s[nt][0] = fmaf(s[nt][0], scl, rc0[ca]);
+        s[nt][1] = fmaf(s[nt][1], scl, rc0[cb]);
+        s[nt][2] = fmaf(s[nt][2], scl, rc1[ca]);
+        s[nt][3] = fmaf(s[nt][3], scl, rc1[cb]);
         mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
         mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
       }
@@ -572,13 +591,13 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
 #pragma unroll
       for (int nt = 0; nt < 18; ++nt) {
         const int kj = nt * 8 + 2 * t4;
-        const float2 b0 = __ldg(reinterpret_cast<const float2*>(rel0 + kj));
-        const float2 b1 = __ldg(reinterpret_cast<const float2*>(rel1 + kj));
+        const int c2 = *reinterpret_cast<const int*>(&coff[kj]);
+        const int ca = (short)(c2 & 0xffff), cb = c2 >> 16;
         const int ra = reg[kj], rb = reg[kj + 1];
-        s[nt][0] = fmaf(s[nt][0], scl, b0.x * kLog2e) + (ra != reg0 ? kNeg : 0.f);
-        s[nt][1] = fmaf(s[nt][1], scl, b0.y * kLog2e) + (rb != reg0 ? kNeg : 0.f);
-        s[nt][2] = fmaf(s[nt][2], scl, b1.x * kLog2e) + (ra != reg1 ? kNeg : 0.f);
-        s[nt][3] = fmaf(s[nt][3], scl, b1.y * kLog2e) + (rb != reg1 ? kNeg : 0.f);
+        s[nt][0] = fmaf(s[nt][0], scl, rc0[ca]) + (ra != reg0 ? kNeg : 0.f);
+        s[nt][1] = fmaf(s[nt][1], scl, rc0[cb]) + (rb != reg0 ? kNeg : 0.f);
+        s[nt][2] = fmaf(s[nt][2], scl, rc1[ca]) + (ra != reg1 ? kNeg : 0.f);
+        s[nt][3] = fmaf(s[nt][3], scl, rc1[cb]) + (rb != reg1 ? kNeg : 0.f);
         mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
         mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
       }
@@ -759,7 +778,7 @@ static int launch_window(const void* qkv, const void* qkv_bias, const float* rel
   const int ws = 12;
   const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
   const int nWx = Wp / ws, nW = nWx * (Hp / ws);
-  constexpr size_t smem = sizeof(T) * 2 * 3 * 144 * 40 + sizeof(int) * 144 + 144;
+  constexpr size_t smem = sizeof(T) * 2 * 3 * 144 * 40 + sizeof(int) * 144 + 144 + sizeof(float) * 2 * (529 + 3) + sizeof(short) * 144;
 #define WIN(HPC)                                                                                                  \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \
