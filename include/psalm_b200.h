@@ -91,10 +91,11 @@ int psalm_msda_encoder_fused(const void* value, const void* ow, void* out,
  *   mask of BasicLayer.forward (swin_trans.py:370-387).
  *   qkv      [B, H*W, 3*C]  output of the qkv Linear on norm1(x), UNPADDED and UNSHIFTED token order
  *   qkv_bias [3*C]          value of a zero-padded token after the Linear (swin_trans.py:207-214)
- *   rel_bias [nh, ws*ws, ws*ws] fp32, relative_position_bias_table gathered by relative_position_index
- *            (swin_trans.py:98-114, 137-141).  It MUST be such a gather, i.e. entry (i, j) depends only on the
- *            relative offset of tokens i and j: the tensor-core kernel reads the (2 ws - 1)^2 distinct values of
- *            each head once into shared memory instead of streaming the dense table (83 KB per window-head).
+ *   rel_bias [nh, (2*ws-1)^2] fp32: the checkpoint's relative_position_bias_table TRANSPOSED (head-major).
+ *            Entry (dy + ws - 1) * (2 ws - 1) + (dx + ws - 1) is the bias between a query at window
+ *            position (yi, xi) and a key at (yi - dy, xi - dx) — the value relative_position_index
+ *            (swin_trans.py:93-103) selects for that pair; the dense [ws^2, ws^2] gather (:137-141, 83 KB per
+ *            head) never exists.  Same meaning for every dtype / kernel path.
  *   out      [B, H*W, C]    attention output before `proj`, original token order (padding cropped)
  * ------------------------------------------------------------------------------------------ */
 int psalm_window_attention(const void* qkv, const void* qkv_bias, const float* rel_bias, void* out,

@@ -482,9 +482,9 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
   int* tok = reinterpret_cast<int*>(bufs + 2 * 3 * N * LD);     // [N]
   unsigned char* reg = reinterpret_cast<unsigned char*>(tok + N);  // [N]
   // The relative-position bias of a head has only (2 WS - 1)^2 = 529 distinct values (swin_trans.py:98-114 gathers
-  // them into the dense [N, N] table); reading the dense table costs 83 KB of L2 traffic per (window, head) - 11x
-  // the q/k/v bytes.  The 529 values are picked out of the dense table once per head into shared memory
-  // (pre-multiplied by log2e) and indexed with (row base + column offset).
+  // them into a dense [N, N] table: 83 KB of L2 traffic per (window, head), 11x the q/k/v bytes).  The ABI takes
+  // the compact table; its 529 values are staged once per head into shared memory (pre-multiplied by log2e)
+  // and indexed with (row base + column offset).
   constexpr int NREL = (2 * WS - 1) * (2 * WS - 1);
   float* relc = reinterpret_cast<float*>(reg + N);               // [2 stages][NREL + 3]
   short* coff = reinterpret_cast<short*>(relc + 2 * (NREL + 3)); // [N] column part of the compact index
@@ -522,12 +522,9 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
     }
     cp_async_commit();
   };
-  auto load_rel = [&](int h, int stage) {   // compact bias table of head h: entry (dy, dx) from dense[(i, j)] with i - j = (dy, dx)
-    for (int c = tid; c < NREL; c += 288) {
-      const int dy = c / (2 * WS - 1) - (WS - 1), dx = c % (2 * WS - 1) - (WS - 1);
-      const int i = max(dy, 0) * WS + max(dx, 0), j = max(-dy, 0) * WS + max(-dx, 0);
-      relc[stage * (NREL + 3) + c] = __ldg(rel + ((size_t)h * N + i) * N + j) * kLog2e;
-    }
+  auto load_rel = [&](int h, int stage) {   // compact bias table of head h ((2 WS - 1)^2 entries, index = swin_trans.py:93-103)
+    for (int c = tid; c < NREL; c += 288)
+      relc[stage * (NREL + 3) + c] = __ldg(rel + (size_t)h * NREL + c) * kLog2e;
   };
   prefetch(h0, 0);
   load_rel(h0, 0);
@@ -659,11 +656,10 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
 template <typename T, int HD, typename Policy, int KG>
 static void launch_flash_kg(const Policy& pol, AttnDims dm, float* workspace, cudaStream_t st) {
   constexpr size_t smem = sizeof(T) * (64 * (HD + 8) + (size_t)KG * 4 * 64 * (HD + 8)) + sizeof(unsigned long long) * 128;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static PerDevice once;   // per instantiation and per device
+  if (once.first()) {
     cudaFuncSetAttribute(flash_mma_kernel<T, HD, Policy, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flash_mma_kernel<T, HD, Policy, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr_set = true;
   }
   dim3 grid(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
   flash_mma_kernel<T, HD, Policy, KG><<<grid, 128 * KG, smem, st>>>(pol, dm, workspace);
@@ -675,7 +671,9 @@ template <typename T, int HD, typename Policy, int KG>
 static bool launch_flash_cluster(const Policy& pol, AttnDims dm, cudaStream_t st) {
   constexpr size_t smem = sizeof(T) * (64 * (HD + 8) + (size_t)KG * 4 * 64 * (HD + 8)) + sizeof(unsigned long long) * 128;
   auto kern = flash_mma_kernel<T, HD, Policy, KG, true>;
-  static int max_cluster = -1;   // per instantiation: largest cluster size proven schedulable
+  static PerDevice probe_state;   // per instantiation and device: largest cluster size proven schedulable
+  const bool first_here = probe_state.first();
+  int& max_cluster = probe_state.v[PerDevice::dev()];
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(((dm.Lq + 63) / 64) * dm.splits, dm.H, dm.B);
   cfg.blockDim = dim3(128 * KG);
@@ -688,7 +686,7 @@ static bool launch_flash_cluster(const Policy& pol, AttnDims dm, cudaStream_t st
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (max_cluster < 0) {
+  if (first_here) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -781,11 +779,10 @@ static int launch_window(const void* qkv, const void* qkv_bias, const float* rel
   constexpr size_t smem = sizeof(T) * 2 * 3 * 144 * 40 + sizeof(int) * 144 + 144 + sizeof(float) * 2 * (529 + 3) + sizeof(short) * 144;
 #define WIN(HPC)                                                                                                  \
   do {                                                                                                            \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
+    static PerDevice once;                                                                                        \
+    if (once.first()) {                                                                                           \
       cudaFuncSetAttribute(window_mma_kernel<T, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
       cudaFuncSetAttribute(window_mma_kernel<T, HPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);       \
-      attr_set = true;                                                                                            \
     }                                                                                                             \
     dim3 grid(B * nW, nh / HPC);                                                                                  \
     window_mma_kernel<T, HPC><<<grid, 288, smem, st>>>((const T*)qkv, (const T*)qkv_bias, rel, (T*)out, H, W, Hp,   \

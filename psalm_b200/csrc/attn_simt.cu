@@ -41,7 +41,7 @@ template <typename T>
 struct WindowPolicy {
   const T* qkv;        // [B, H*W, 3, nh, hd]
   const T* qkv_bias;   // [3*C]  (value of a zero-padded token after the qkv Linear)
-  const float* rel;    // [nh, ws*ws, ws*ws] dense relative-position bias
+  const float* rel;    // [nh, (2 ws - 1)^2] compact relative-position bias table (checkpoint table, transposed)
   T* out;              // [B, H*W, C]
   int H, W, Hp, Wp, ws, shift, nh, hd, C, nWx, nW;
 
@@ -69,8 +69,10 @@ struct WindowPolicy {
   __device__ __forceinline__ float4 load_k4(int z, int h, int n, int d0) const { return load(1, z, h, n, d0); }
   __device__ __forceinline__ float4 load_v4(int z, int h, int n, int d0) const { return load(2, z, h, n, d0); }
   __device__ __forceinline__ float score(int z, int h, int qi, int kj, float s) const {
-    const int N = ws * ws;
-    s += __ldg(rel + ((size_t)h * N + qi) * N + kj);
+    // relative_position_index[qi, kj] = (yi - yj + ws - 1) * (2 ws - 1) + (xi - xj + ws - 1)  (swin_trans.py:93-103)
+    const int R = 2 * ws - 1;
+    const int yi = qi / ws, xi = qi - yi * ws, yj = kj / ws, xj = kj - yj * ws;
+    s += __ldg(rel + (size_t)h * R * R + (yi - yj + ws - 1) * R + (xi - xj + ws - 1));
     if (shift > 0) {
       int t, rq, rk;
       token(z, qi, t, rq);

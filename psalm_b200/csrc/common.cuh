@@ -32,6 +32,16 @@ inline int check_launch(const char* what) {
 
 inline size_t dtype_size(int dt) { return dt == PSALM_F32 ? 4 : 2; }
 
+// cudaFuncSetAttribute / cluster-occupancy probes are PER DEVICE: a once-per-process flag would leave the second
+// GPU of a process unconfigured (kernels needing > 48 KB of dynamic shared memory then fail to launch there).
+struct PerDevice {
+  int v[64];
+  bool set[64];
+  PerDevice() { for (int i = 0; i < 64; ++i) { v[i] = 0; set[i] = false; } }
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool first() { const int d = dev(); if (set[d]) return false; set[d] = true; return true; }
+};
+
 // ---- element conversion -------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -34,6 +34,21 @@ def _count(n=1):
     _LAUNCHES[0] += n
 
 
+def _on_device(fn):
+    """Launch on the device that owns the first tensor argument (the C ABI launches on the CURRENT device; a model
+    on cuda:1 while cuda:0 is current would otherwise fail or, worse, launch with foreign pointers)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapper
+
+
 def _chk(t, name):
     if not t.is_cuda:
         raise _lib.PsalmKernelError("%s: expected a CUDA tensor, got %s (no CPU path)" % (name, t.device))
@@ -41,12 +56,13 @@ def _chk(t, name):
         raise _lib.PsalmKernelError("%s: tensor must be contiguous" % name)
 
 
+@_on_device
 def window_attention(qkv, qkv_bias, rel_bias, B, H, W, C, nh, ws, shift):
     """qkv [B,H*W,3C] -> attention output [B,H*W,C] (before proj).  swin_trans.py:117-149,194-253."""
     for t, n in ((qkv, "qkv"), (qkv_bias, "qkv_bias"), (rel_bias, "rel_bias")):
         _chk(t, "window_attention." + n)
-    if rel_bias.dtype != torch.float32 or tuple(rel_bias.shape) != (nh, ws * ws, ws * ws):
-        raise _lib.PsalmKernelError("window_attention: rel_bias must be fp32 [nh, ws^2, ws^2]")
+    if rel_bias.dtype != torch.float32 or tuple(rel_bias.shape) != (nh, (2 * ws - 1) ** 2):
+        raise _lib.PsalmKernelError("window_attention: rel_bias must be the compact fp32 table [nh, (2*ws-1)^2]")
     if qkv_bias.dtype != qkv.dtype or tuple(qkv.shape) != (B, H * W, 3 * C):
         raise _lib.PsalmKernelError("window_attention: bad qkv / bias")
     out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
@@ -58,6 +74,7 @@ def window_attention(qkv, qkv_bias, rel_bias, B, H, W, C, nh, ws, shift):
     return out
 
 
+@_on_device
 def rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd):
     _chk(qkv, "rotary.qkv")
     _chk(cos, "rotary.cos")
@@ -68,6 +85,7 @@ def rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd):
     _count()
 
 
+@_on_device
 def causal_attention(qkv, key_valid, B, T, nh, hd):
     """qkv [B,T,3,nh,hd] (rotary applied) -> [B,T,nh*hd]; key_valid uint8 [B,T] or None."""
     _chk(qkv, "causal_attention.qkv")
@@ -93,6 +111,7 @@ def pick_splits(B, nh, Lq, Lk):
     return int(max(1, min(want, (Lk + 255) // 256, 16)))
 
 
+@_on_device
 def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, workspace=None):
     """q [B,Lq,C], k/v [B,Lk,C] (already projected) -> [B,Lq,C]."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -117,6 +136,7 @@ def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, w
     return out
 
 
+@_on_device
 def mask_logits(mask_embed, feats, out_dtype=None):
     """mask_embed [B,Q,C], feats [B,P,C] (token-major) -> [B,Q,P]."""
     _chk(mask_embed, "mask_logits.mask_embed")
@@ -133,6 +153,7 @@ def mask_logits(mask_embed, feats, out_dtype=None):
     return out
 
 
+@_on_device
 def bilinear_tokens(x, Hi, Wi, Ho, Wo, out=None, out_dtype=None, accumulate=False):
     """x [B,Hi*Wi,C] token-major -> [B,Ho*Wo,C]; F.interpolate(bilinear, align_corners=False) semantics."""
     _chk(x, "bilinear_tokens.x")
@@ -151,6 +172,7 @@ def bilinear_tokens(x, Hi, Wi, Ho, Wo, out=None, out_dtype=None, accumulate=Fals
     return out
 
 
+@_on_device
 def attn_mask_bits(logits):
     """logits [B,Q,P] -> (bits uint32 [B,Q,ceil(P/32)] (as int32 tensor), row_open uint8 [B,Q])."""
     _chk(logits, "attn_mask_bits.logits")
@@ -167,6 +189,7 @@ def attn_mask_bits(logits):
 _LN_WIDTHS = (128, 256, 512, 1024, 2048)
 
 
+@_on_device
 def add_layer_norm(x, weight, bias, eps=1e-5, r1=None, r2=None, return_sum=False):
     """y = LayerNorm(x + r1 + r2) (residuals optional); with return_sum also returns the summed stream."""
     C = x.shape[-1]
@@ -190,6 +213,7 @@ def add_layer_norm(x, weight, bias, eps=1e-5, r1=None, r2=None, return_sum=False
     return (s, y) if return_sum else y
 
 
+@_on_device
 def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False, pre_bias=None):
     """GroupNorm(groups) (+ReLU) of a token-major map [B,N,C]; `pre_bias` [C] = bias of the producing conv / Linear,
     added inside the kernel (GroupNorm(x + pre_bias))."""
@@ -207,6 +231,7 @@ def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False, pre_bias
     return y
 
 
+@_on_device
 def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0):
     """logits [Q,H4,W4] -> dict(sem_seg, ids, in_mask, inst_masks, stats [Q,5]) at output size (H, W).
     stats columns: count(x>0), sum(sigmoid*[x>0]), count(x>=0), panoptic area, panoptic intersection."""
@@ -243,6 +268,7 @@ def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=Non
     return out
 
 
+@_on_device
 def mask_bits(mask_embed, feats):
     """Attention mask of the next decoder layer from (mask_embed [B,Q,C], pooled feats [B,P,C]):
     (bits int32 [B,Q,ceil(P/32)], row_open uint8 [B,Q]).  16-bit storage: one tensor-core kernel that never

@@ -120,14 +120,19 @@ class MSDeformAttnPixelDecoder:
         # (src + pos) W^T + b = src W^T + (pos W^T + b): the position term is input independent, so it is
         # projected once per (shapes, batch) and enters the GEMM as its additive C matrix; the per-layer
         # broadcast add and the `q` tensor (ms_deform_attn.py:57-58 with_pos_embed) do not exist
+        # keyed by (shapes, batch) and never evicted: captured CUDA graphs hold these device pointers, so an entry
+        # must stay alive (and unmoved) for as long as any graph of that size may be replayed
         pkey = (tuple(shapes), B)
-        if getattr(self, "_pos_ow_key", None) != pkey:
+        if not hasattr(self, "_pos_ow_cache"):
+            self._pos_ow_cache = {}
+        pos_ow = self._pos_ow_cache.get(pkey)
+        if pos_ow is None:
             p32 = pos[0].float()
-            self._pos_ow = [(p32 @ w["e%d.ow.w" % i].float().t() + w["e%d.ow.b" % i].float()).to(self.dtype)
-                            .repeat(B, 1).contiguous() for i in range(cfg.enc_layers)]
-            self._pos_ow_key = pkey
+            pos_ow = [(p32 @ w["e%d.ow.w" % i].float().t() + w["e%d.ow.b" % i].float()).to(self.dtype)
+                      .repeat(B, 1).contiguous() for i in range(cfg.enc_layers)]
+            self._pos_ow_cache[pkey] = pos_ow
         for i in range(cfg.enc_layers):
-            ow = torch.addmm(self._pos_ow[i], src.view(B * S, -1), w["e%d.ow.w" % i].t()).view(B, S, -1)
+            ow = torch.addmm(pos_ow[i], src.view(B * S, -1), w["e%d.ow.w" % i].t()).view(B, S, -1)
             value = F.linear(src, w["e%d.vp.w" % i], w["e%d.vp.b" % i])
             value_hm = value.view(B, S, M, D).permute(0, 2, 1, 3).contiguous()
             a = kernels.timed_msda(kernels.msda_encoder_fused, value_hm, ow.contiguous(), shapes, starts, cfg.enc_points)

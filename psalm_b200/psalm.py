@@ -19,6 +19,9 @@ How it differs from the reference on purpose (results are unchanged, see DESIGN.
   * every image of the batch is post-processed (the reference returns inside the loop, llava_phi.py:1472);
   * no CPU / PyTorch fallback for the hot operators: a missing CUDA library raises.
 """
+import contextlib
+from collections import OrderedDict
+
 import torch
 import torch.nn.functional as F
 
@@ -56,9 +59,6 @@ class PSALM:
         self.use_cuda_graph = use_cuda_graph
         # one fused kernel for the task heads (16-bit storage); fp32 parity runs keep the exact torch path
         self.fused_postprocess = dtype != torch.float32
-        if dtype == torch.float32:  # true fp32 for parity runs (cuDNN would otherwise pick TF32)
-            torch.backends.cudnn.allow_tf32 = False
-            torch.backends.cuda.matmul.allow_tf32 = False
         self.cfg, self.dtype, self.device = cfg, dtype, torch.device(device)
         sd = state_dict
         cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
@@ -72,6 +72,21 @@ class PSALM:
         self.test_topk_per_image = cfg.mask.num_queries
         self.size_divisibility = cfg.mask.size_divisibility
         self.set_task(seg_task)
+
+    @contextlib.contextmanager
+    def _precision_scope(self):
+        """fp32 models run true fp32 library GEMMs / convolutions (cuDNN and cuBLAS would otherwise pick TF32);
+        the global switches are restored on exit, other models in the process are not affected."""
+        if self.dtype != torch.float32:
+            yield
+            return
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            yield
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
     @staticmethod
     def _check_runtime(device):
@@ -105,12 +120,14 @@ class PSALM:
 
     def encode_images(self, images):
         """llava_phi.py:448-451."""
-        feats = self.get_vision_tower()(images)
-        return self.model.mm_projector(feats[-1])
+        with self._precision_scope():
+            feats = self.get_vision_tower()(images)
+            return self.model.mm_projector(feats[-1])
 
     def get_vision_tower_feature(self, images):
         """llava_phi.py:222-230."""
-        f = self.get_vision_tower()(images)
+        with self._precision_scope():
+            f = self.get_vision_tower()(images)
         return dict(res2=f[0], res3=f[1], res4=f[2], res5=f[3])
 
     # ---- the hot path -----------------------------------------------------------------------------
@@ -118,6 +135,10 @@ class PSALM:
     def forward_core(self, images, plan):
         """Device-only part of eval_seg: images [B,3,H,W] on device, `plan` a SequencePlan on device.
         Returns dict(pred_masks [B,Q,H4*W4], mask_size, pred_class_name_logits, pred_SEG_logits)."""
+        with self._precision_scope():
+            return self._forward_core(images, plan)
+
+    def _forward_core(self, images, plan):
         toks, sizes = self.model.vision_tower.forward_tokens(images)                 # Swin, once
         h5, w5 = sizes[3]
         res5 = toks[3].view(toks[3].shape[0], h5, w5, -1).permute(0, 3, 1, 2)
@@ -155,18 +176,22 @@ class PSALM:
                                 self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
                                 self.test_topk_per_image, self.cfg.mask.object_mask_threshold) for b in range(B)]
 
-    def forward_core_graphed(self, images, plan, lane=0):
+    MAX_GRAPHS = 8   # each entry owns static buffers + a private pool (hundreds of MB at 1024^2, B = 4)
+
+    def forward_core_graphed(self, images, plan, lane=0, fuse_post=True):
         """Same results as forward_core, replayed from a CUDA graph captured per (image size, prompt
         structure): the ~800 launches of one image become one graph launch (the reference issues them
         one by one from Python, plus ~150 extra tiny launches in its decoder).  `lane` selects an
         independent graph + static buffers so that several images can be in flight on different streams."""
-        key = (lane, self.seg_task, tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), plan.B,
+        key = (lane, bool(fuse_post), self.seg_task, tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), plan.B,
                plan.T, plan.n_img, plan.any_padding,
                None if plan.cls_pool is None else tuple(plan.cls_pool.shape), plan.refer_pool is not None,
                None if plan.pad_pos is None else int(plan.pad_pos.numel()))
         if not hasattr(self, "_graphs"):
-            self._graphs = {}
+            self._graphs = OrderedDict()
         ent = self._graphs.get(key)
+        if ent is not None:
+            self._graphs.move_to_end(key)
         tensors = ("tok_ids", "img_pos", "seg_pos", "pad_pos", "attention_mask", "cls_pool", "refer_pool")
         if ent is None:
             import copy
@@ -181,14 +206,17 @@ class PSALM:
             with torch.cuda.stream(side):
                 for _ in range(2):
                     o = self.forward_core(static_img, static_plan)
-                    o["post"] = self._post_device(o, hw)
+                    o["post"] = self._post_device(o, hw) if fuse_post else None
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = self.forward_core(static_img, static_plan)
-                static_out["post"] = self._post_device(static_out, hw)   # task heads' device part, same graph
+            with self._precision_scope(), torch.cuda.graph(g):
+                static_out = self._forward_core(static_img, static_plan)
+                # task heads' device part in the same graph (only when every image takes the fused path)
+                static_out["post"] = self._post_device(static_out, hw) if fuse_post else None
             ent = (g, static_img, static_plan, static_out)
+            while len(self._graphs) >= self.MAX_GRAPHS:   # least recently used graph and its static buffers go
+                self._graphs.popitem(last=False)
             self._graphs[key] = ent
         g, static_img, static_plan, static_out = ent
         static_img.copy_(images, non_blocking=True)
@@ -246,12 +274,32 @@ class PSALM:
         images_d = images.to(self.device, non_blocking=True)
         plan = self._cached_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
                                  class_name_embedding_indices, token_refer_id, refer_embedding_indices)
-        out = self.forward_core_graphed(images_d, plan) if self.use_cuda_graph else self.forward_core(images_d, plan)
-        return self.post_process(out, images.shape[-2:], seg_info)
+        fused, boxes = self._fused_applies(images.shape[-2:], seg_info)
+        if self.use_cuda_graph:
+            out = self.forward_core_graphed(images_d, plan, fuse_post=fused)
+        else:
+            out = self.forward_core(images_d, plan)
+        return self.post_process(out, images.shape[-2:], seg_info, boxes)
+
+    def _fused_applies(self, image_hw, seg_info):
+        """True when every image of the batch takes the fused task-head kernel (no crop, output size == padded
+        input size); otherwise the graph is captured without the fused kernel instead of running it for nothing."""
+        Hi, Wi = image_hw
+        d = self.size_divisibility
+        Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d
+        boxes = [PP.unpadded_box(info["padding_mask"]) for info in seg_info]
+        fused = all((info.get("height", Hi), info.get("width", Wi)) == (Hp, Wp) and box == (Hp, Wp)
+                    for info, box in zip(seg_info, boxes))
+        return fused, boxes
 
     @torch.no_grad()
-    def post_process(self, out, image_hw, seg_info):
-        """llava_phi.py:1395-1472 for EVERY image of the batch."""
+    def post_process(self, out, image_hw, seg_info, boxes=None):
+        """llava_phi.py:1395-1472 for EVERY image of the batch.  `boxes`: un-padded (h, w) per image when the
+        caller already derived them from the padding masks."""
+        with self._precision_scope():
+            return self._post_process(out, image_hw, seg_info, boxes)
+
+    def _post_process(self, out, image_hw, seg_info, boxes=None):
         Hi, Wi = image_hw
         d = self.size_divisibility
         Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d     # ImageList.from_tensors(images, 32), :1400
@@ -263,7 +311,7 @@ class PSALM:
         for b in range(B):
             info = seg_info[b]
             height, width = info.get("height", Hi), info.get("width", Wi)
-            oh, ow = PP.unpadded_box(info["padding_mask"])
+            oh, ow = boxes[b] if boxes is not None else PP.unpadded_box(info["padding_mask"])
             cls_b = out["pred_class_name_logits"][b] if out["pred_class_name_logits"] is not None else None
             seg_b = out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None
             trivial = (oh, ow) == (Hp, Wp) and (height, width) == (Hp, Wp)

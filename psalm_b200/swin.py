@@ -7,13 +7,28 @@ four stage outputs (strides 4/8/16/32), each through its own LayerNorm.  Differe
     partition, the zero padding after norm1 (swin_trans.py:207-214), the relative-position bias gather
     (:131-134) and the -100 shift mask (:370-387) are folded into the kernel's addressing, so the
     reference's roll / pad / partition / reverse copies do not exist;
-  * the relative-position bias is gathered once at weight-preparation time into a dense fp32 table.
+  * the relative-position bias stays the compact (2 ws - 1)^2 table of the checkpoint (transposed, fp32).
 Linear layers are library GEMMs (cuBLAS through torch)."""
 import torch
 import torch.nn.functional as F
 
 from . import kernels
 from .layout import SwinConfig
+
+
+_REL_INDEX = {}
+
+
+def _rel_index(ws):
+    """relative_position_index of a ws x ws window (swin_trans.py:93-103)."""
+    if ws not in _REL_INDEX:
+        coords = torch.stack(torch.meshgrid([torch.arange(ws), torch.arange(ws)], indexing="ij")).flatten(1)
+        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += ws - 1
+        rel[:, :, 1] += ws - 1
+        rel[:, :, 0] *= 2 * ws - 1
+        _REL_INDEX[ws] = rel.sum(-1)
+    return _REL_INDEX[ws]
 
 
 class SwinTransformer:
@@ -36,10 +51,14 @@ class SwinTransformer:
                 for n in ("norm1", "norm2", "attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2"):
                     w[p + n + ".w"] = cv(g(p + n + ".weight"))
                     w[p + n + ".b"] = cv(g(p + n + ".bias"))
-                idx = g(p + "attn.relative_position_index").view(-1).long()
+                # compact table [nh, (2 ws - 1)^2] fp32; the kernels index it like relative_position_index does
+                # (swin_trans.py:93-103, a deterministic buffer: it is validated if the checkpoint carries it,
+                # never needed)
                 tab = g(p + "attn.relative_position_bias_table").float()
-                # [ws^2*ws^2, nh] -> [nh, ws^2, ws^2] fp32 (swin_trans.py:131-134)
-                w[p + "rel"] = tab[idx].view(ws * ws, ws * ws, nh).permute(2, 0, 1).contiguous().to(device)
+                idx = sd.get(prefix + p + "attn.relative_position_index")
+                if idx is not None and not torch.equal(idx.cpu().long(), _rel_index(ws)):
+                    raise ValueError("%sattn.relative_position_index differs from swin_trans.py:93-103" % (prefix + p))
+                w[p + "rel"] = tab.t().contiguous().to(device)
             if s < len(cfg.depths) - 1:
                 p = "layers.%d.downsample." % s
                 w[p + "red.w"] = cv(g(p + "reduction.weight"))

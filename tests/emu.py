@@ -20,7 +20,9 @@ def window_attention(qkv, qkv_bias, rel_bias, B, H, W, C, nh, ws, shift):
         x = torch.roll(x, (-shift, -shift), (1, 2))
     xw = O._window_partition(x, ws).view(-1, ws * ws, 3, nh, hd).permute(2, 0, 3, 1, 4).float()
     q, k, v = xw[0], xw[1], xw[2]
-    attn = (q @ k.transpose(-2, -1)) * hd ** -0.5 + rel_bias.unsqueeze(0)
+    # rel_bias is the compact [nh, (2 ws - 1)^2] table; expand it the way the reference does (swin_trans.py:131-134)
+    dense = rel_bias[:, O.relative_position_index(ws).view(-1)].view(nh, ws * ws, ws * ws)
+    attn = (q @ k.transpose(-2, -1)) * hd ** -0.5 + dense.unsqueeze(0)
     if shift:
         m = O._shift_mask(H, W, ws, shift)
         nW = m.shape[0]

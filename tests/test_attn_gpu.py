@@ -35,12 +35,9 @@ def test_window_attention(dt, H, W, shift):
     B, C, nh, ws = 2, 64, 2, 12
     qkv = torch.randn(B, H * W, 3 * C).to(DT[dt])
     bias = (torch.randn(3 * C) * 0.5).to(DT[dt])
-    # relative-position bias: dense [nh, N, N] expansion of a (2 ws - 1)^2 table, as Swin builds it (swin_trans.py:98-114)
-    table = torch.randn(nh, (2 * ws - 1) ** 2)
-    yy, xx = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")
-    yy, xx = yy.flatten(), xx.flatten()
-    ridx = (yy[:, None] - yy[None, :] + ws - 1) * (2 * ws - 1) + (xx[:, None] - xx[None, :] + ws - 1)
-    rel = table[:, ridx].contiguous()
+    # compact relative-position bias table (the checkpoint's relative_position_bias_table, transposed); the emulation
+    # expands it with the reference's relative_position_index (swin_trans.py:93-103, 131-134)
+    rel = torch.randn(nh, (2 * ws - 1) ** 2)
     ref = emu.window_attention(qkv.float(), bias.float(), rel, B, H, W, C, nh, ws, shift)
     out = kernels.window_attention(qkv.cuda(), bias.cuda(), rel.cuda(), B, H, W, C, nh, ws, shift)
     _close(out, ref, dt)
