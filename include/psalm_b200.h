@@ -24,7 +24,7 @@ extern "C" {
 #define PSALM_ABI_VERSION 1
 
 /* element types */
-enum { PSALM_F32 = 0, PSALM_F16 = 1, PSALM_BF16 = 2 };
+enum { PSALM_F32 = 0, PSALM_F16 = 1, PSALM_BF16 = 2, PSALM_U8 = 3 };
 
 /* error codes */
 enum {
@@ -192,6 +192,20 @@ int psalm_postproc_fused(const void* logits, const void* probsT_f16, const float
                          const int* slot_query, float* sem_seg, float* inst_masks, int* ids,
                          unsigned char* in_mask, float* partials, int Q, int H4, int W4, int H, int W, int ncls,
                          int K, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input pipeline on the device: pixel normalisation + zero padding to the patch grid +
+ * unfold into the operand of the patch-embedding GEMM, one pass.
+ * Replaces: `(image - pixel_mean) / pixel_std` on the host (datasets_mapper/coco_panoptic_mapper.py:161; the
+ *   image can then be uploaded as uint8), PatchEmbed's F.pad and the unfold inside its stride-4 convolution
+ *   (multimodal_encoder/swin_trans.py:427-441).
+ *   images  [B,Cin,H,W] in_dtype (PSALM_U8 / F32 / F16 / BF16)
+ *   mean, stdv [Cin] fp32 or both NULL (input already normalised)
+ *   patches [B, ceil(H/4)*ceil(W/4), Cin*16] out_dtype; element (c,i,j) of patch (py,px) is the normalised
+ *           pixel (c, 4py+i, 4px+j), 0 beyond the image border (zero padding AFTER normalisation, as F.pad does).
+ * ------------------------------------------------------------------------------------------ */
+int psalm_patchify(const void* images, void* patches, const float* mean, const float* stdv, int B, int Cin,
+                   int H, int W, int patch, int in_dtype, int out_dtype, void* stream);
 
 #ifdef __cplusplus
 }

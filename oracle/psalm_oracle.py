@@ -601,9 +601,11 @@ def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8):
 # ------------------------------------------------------------------------------------------------
 def eval_seg(sd, input_ids, attention_mask, images, seg_info, class_name_ids=None, cls_indices=None,
              class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None,
-             is_thing_list=None, task="panoptic", phi_cfg=PHI_15, return_intermediates=False):
+             is_thing_list=None, task="panoptic", phi_cfg=PHI_15, return_intermediates=False,
+             obj_thr=0.8, ovl_thr=0.8):
     """Returns list (one dict per image).  NOTE the reference returns after image 0 (LP:1472);
-    we process every image the same way."""
+    we process every image the same way.  obj_thr / ovl_thr: the panoptic thresholds the reference hard-codes
+    to 0.8 / 0.8 (LP:331-332); other values only in accuracy runs on random weights (oracle/accuracy.py)."""
     feats = swin_forward(sd, "model.vision_tower.", images)  # the reference runs this twice (LP:449, LP:223)
     img_tok = projector_forward(sd, "model.mm_projector.", feats[3])
     seq = assemble_sequence(sd, input_ids, attention_mask, img_tok, class_name_ids, cls_indices,
@@ -643,7 +645,8 @@ def eval_seg(sd, input_ids, attention_mask, images, seg_info, class_name_ids=Non
             r["instances"] = instance_inference(po["pred_class_name_logits"][b].float(), mp.float(),
                                                 po["pred_masks"].shape[1], is_thing_list, task == "panoptic")
         if task == "panoptic":
-            r["panoptic_seg"] = panoptic_inference(po["pred_class_name_logits"][b].float(), mp.float(), is_thing_list)
+            r["panoptic_seg"] = panoptic_inference(po["pred_class_name_logits"][b].float(), mp.float(), is_thing_list,
+                                                   obj_thr, ovl_thr)
         if task == "referring":
             r["instances"] = seg_instance_inference(po["pred_SEG_logits"][b].float(), mp.float(),
                                                     po["pred_masks"].shape[1])

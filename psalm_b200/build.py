@@ -21,45 +21,56 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stamp():
+def _hash(paths, extra=""):
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)) + ["../../include/psalm_b200.h"]:
-        p = os.path.join(CSRC, f)
-        if os.path.isfile(p):
-            h.update(f.encode())
-            h.update(open(p, "rb").read())
-    h.update(" ".join(FLAGS).encode())
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    h.update(extra.encode())
     return h.hexdigest()
 
 
+def _shared_headers():
+    hdrs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    return hdrs + [os.path.join(HERE, "..", "include", "psalm_b200.h")]
+
+
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
-    stamp_file = LIB + ".stamp"
-    stamp = _stamp()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
-        return LIB
-    objs = []
-    procs = []
+    """Compile every .cu under csrc/ into one shared library (incrementally: an object is rebuilt only when its
+    source, a shared header or the flags changed).  Returns the library path."""
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    hdrs = _shared_headers()
+    objs, procs, stamps = [], [], {}
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        stamp = _hash([src] + hdrs, " ".join(FLAGS))
+        stamps[obj] = stamp
         objs.append(obj)
+        sf = obj + ".stamp"
+        if not force and os.path.exists(obj) and os.path.exists(sf) and open(sf).read() == stamp:
+            continue
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
-    for src, p in procs:
+    for src, obj, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             failed = True
             sys.stderr.write("nvcc failed for %s:\n%s\n" % (src, out))
-        elif verbose or out.strip():
-            sys.stderr.write(out)
+        else:
+            with open(obj + ".stamp", "w") as f:
+                f.write(stamps[obj])
+            if verbose or out.strip():
+                sys.stderr.write(out)
     if failed:
         raise RuntimeError("psalm_b200: CUDA build failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
-    subprocess.check_call(cmd)
+    lib_stamp = hashlib.sha256("".join(stamps[o] for o in objs).encode()).hexdigest()
+    stamp_file = LIB + ".stamp"
+    if not procs and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == lib_stamp:
+        return LIB
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
     with open(stamp_file, "w") as f:
-        f.write(stamp)
+        f.write(lib_stamp)
     return LIB
 
 

@@ -1,8 +1,12 @@
 """Multi-GPU plumbing of the hot path: images are independent units, so ranks hold full
-weight replicas, take disjoint images and meet only twice — a MAX reduction of the device-timed step
-time and ONE all_gather of fixed-size per-image prediction records (what the reference *would* do with
-detectron2.comm.all_gather, psalm/eval/segmentation_evaluation/referring_evaluation.py:162-164, but never
-enables).  Backend: NCCL over NVLink on GPUs, gloo in the CPU tests."""
+weight replicas and take disjoint images; there is no collective on the data path.  What crosses NVLink is what
+the evaluators consume (what the reference *would* do with detectron2.comm.all_gather,
+psalm/eval/segmentation_evaluation/referring_evaluation.py:162-164, but never enables):
+  * per step, ONE all_gather of the fixed-size predictions of every image — class_id[Q], score[Q] and the int32
+    panoptic id map [H,W] (`pack_predictions` / `gather_predictions`);
+  * an all_reduce(SUM) of metric accumulators (confusion matrix, PQ tp/fp/fn/iou) (`reduce_sum`);
+  * a MAX reduction of the device-timed step time (`max_over_ranks`).
+Backend: NCCL over NVLink on GPUs, gloo in the CPU tests."""
 import torch
 import torch.distributed as dist
 
@@ -40,3 +44,51 @@ def gather_records(local):
     out = [torch.empty_like(local) for _ in range(dist.get_world_size())]
     dist.all_gather(out, local.contiguous())
     return torch.cat(out, 0)
+
+
+def pack_predictions(results, num_queries=100):
+    """Per-image fixed-size payload of the prediction gather: meta [n, Q, 2] fp32 = (score, class id)
+    of the instance predictions (zero padded, class -1 = empty slot) and the panoptic id map [n, H, W] int32
+    (None when the task has no panoptic output)."""
+    metas, maps = [], []
+    for r in results:
+        inst = r.get("instances")
+        dev = (inst.scores if inst is not None else r["panoptic_seg"][0]).device
+        meta = torch.zeros(num_queries, 2, dtype=torch.float32, device=dev)
+        meta[:, 1] = -1.0
+        if inst is not None:
+            n = min(num_queries, inst.scores.shape[0])
+            meta[:n, 0] = inst.scores[:n]
+            meta[:n, 1] = inst.pred_classes[:n].float() if inst.has("pred_classes") else 0.0
+        metas.append(meta)
+        if "panoptic_seg" in r:
+            maps.append(r["panoptic_seg"][0])
+    return torch.stack(metas), (torch.stack(maps) if maps else None)
+
+
+def gather_predictions(meta, maps):
+    """all_gather of the per-step predictions: ([world*n, Q, 2], [world*n, H, W] or None), rank order."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return meta, maps
+    world = dist.get_world_size()
+    out = []
+    for t in (meta, maps):
+        if t is None:
+            out.append(None)
+            continue
+        t = t.contiguous()
+        g = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(g, t)
+        out.append(g)
+    return out[0], out[1]
+
+
+def reduce_sum(tensors, device):
+    """all_reduce(SUM) of metric accumulators (list of tensors, returned on `device`)."""
+    outs = []
+    for t in tensors:
+        t = t.to(device)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        outs.append(t)
+    return outs

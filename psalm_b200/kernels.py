@@ -298,3 +298,24 @@ def linear_act(x, weight, bias, act):
         return y.view(*shp[:-1], weight.shape[0])
     y = F.linear(x, weight, bias)
     return F.relu(y) if act == "relu" else F.gelu(y, approximate="tanh")
+
+
+@_on_device
+def patchify(images, out_dtype, mean=None, std=None, patch=4):
+    """images [B,Cin,H,W] (uint8 / float) -> patches [B, ceil(H/4)*ceil(W/4), Cin*16] in out_dtype, normalised with
+    (x - mean) / std when given, zero padded to the patch grid.  coco_panoptic_mapper.py:161 + swin_trans.py:427-441."""
+    _chk(images, "patchify.images")
+    B, Cin, H, W = images.shape
+    Wh, Ww = -(-H // patch), -(-W // patch)
+    out = torch.empty((B, Wh * Ww, Cin * patch * patch), dtype=out_dtype, device=images.device)
+    if (mean is None) != (std is None):
+        raise _lib.PsalmKernelError("patchify: mean and std come together")
+    for t in (mean, std):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != Cin or not t.is_cuda):
+            raise _lib.PsalmKernelError("patchify: mean / std must be fp32 CUDA tensors of %d values" % Cin)
+    rc = _lib.lib().psalm_patchify(_lib.ptr(images), _lib.ptr(out), _lib.ptr(mean) if mean is not None else None,
+                                   _lib.ptr(std) if std is not None else None, B, Cin, H, W, patch,
+                                   _lib.dtype_code(images.dtype), _lib.dtype_code(out_dtype), _lib.stream_ptr(images.device))
+    _lib.check(rc, "psalm_patchify")
+    _count()
+    return out, (Wh, Ww)

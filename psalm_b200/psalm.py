@@ -35,6 +35,16 @@ from .projector import ResNetSwin
 from .swin import SwinTransformer
 
 
+class StagedImages:
+    """A batch of images whose host->device copy was enqueued on the model's copy stream by
+    `PSALM.stage_images`; `PSALM.eval_seg(images=staged, ...)` waits for it on the compute stream."""
+
+    def __init__(self, slot, ready):
+        self.slot, self.ready = slot, ready          # slot = [device buffer, event "consumer is done"]
+        self.tensor = slot[0]
+        self.shape, self.dtype = slot[0].shape, slot[0].dtype
+
+
 class PSALMModel:
     """`model.model` of the reference (PSALMModel(LlavaMetaModel, PhiModel), llava_phi.py:52): owns the
     LLM, the vision tower and the projector."""
@@ -71,6 +81,9 @@ class PSALM:
         self.num_queries = cfg.mask.num_queries
         self.test_topk_per_image = cfg.mask.num_queries
         self.size_divisibility = cfg.mask.size_divisibility
+        # panoptic thresholds: the reference hard-codes 0.8 / 0.8 (llava_phi.py:331-332)
+        self.object_mask_threshold = cfg.mask.object_mask_threshold
+        self.overlap_threshold = cfg.mask.overlap_threshold
         self.set_task(seg_task)
 
     @contextlib.contextmanager
@@ -132,13 +145,14 @@ class PSALM:
 
     # ---- the hot path -----------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_core(self, images, plan):
+    def forward_core(self, images, plan, trace=None):
         """Device-only part of eval_seg: images [B,3,H,W] on device, `plan` a SequencePlan on device.
-        Returns dict(pred_masks [B,Q,H4*W4], mask_size, pred_class_name_logits, pred_SEG_logits)."""
+        Returns dict(pred_masks [B,Q,H4*W4], mask_size, pred_class_name_logits, pred_SEG_logits).
+        `trace`: optional dict that receives the stage outputs (token-major), for the per-stage parity tests."""
         with self._precision_scope():
-            return self._forward_core(images, plan)
+            return self._forward_core(images, plan, trace)
 
-    def _forward_core(self, images, plan):
+    def _forward_core(self, images, plan, trace=None):
         toks, sizes = self.model.vision_tower.forward_tokens(images)                 # Swin, once
         h5, w5 = sizes[3]
         res5 = toks[3].view(toks[3].shape[0], h5, w5, -1).permute(0, 3, 1, 2)
@@ -154,6 +168,9 @@ class PSALM:
         mask_features, ms, ms_sizes = self.pixel_decoder.forward_tokens(toks, sizes)
         out = self.predictor.forward_tokens(ms, ms_sizes, mask_features, sizes[0], seg_q, SEG_emb, cls_emb)
         out["mask_size"] = sizes[0]
+        if trace is not None:
+            trace.update(swin=toks, swin_sizes=sizes, img_tok=img_tok, embeds=embeds, hidden=hidden, seg_query=seg_q,
+                         SEG_emb=SEG_emb, cls_emb=cls_emb, mask_features=mask_features, ms=ms, ms_sizes=ms_sizes)
         return out
 
     # ---- CUDA-graph replay of the device-only part -------------------------------------------------
@@ -174,7 +191,7 @@ class PSALM:
         return [PP.fused_device(kernels, pm[b], Hp, Wp, cls[b] if cls is not None else None,
                                 out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None, thing,
                                 self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
-                                self.test_topk_per_image, self.cfg.mask.object_mask_threshold) for b in range(B)]
+                                self.test_topk_per_image, self.object_mask_threshold) for b in range(B)]
 
     MAX_GRAPHS = 8   # each entry owns static buffers + a private pool (hundreds of MB at 1024^2, B = 4)
 
@@ -183,7 +200,7 @@ class PSALM:
         structure): the ~800 launches of one image become one graph launch (the reference issues them
         one by one from Python, plus ~150 extra tiny launches in its decoder).  `lane` selects an
         independent graph + static buffers so that several images can be in flight on different streams."""
-        key = (lane, bool(fuse_post), self.seg_task, tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), plan.B,
+        key = (lane, bool(fuse_post), self.seg_task, float(self.object_mask_threshold), tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), str(images.dtype), plan.B,
                plan.T, plan.n_img, plan.any_padding,
                None if plan.cls_pool is None else tuple(plan.cls_pool.shape), plan.refer_pool is not None,
                None if plan.pad_pos is None else int(plan.pad_pos.numel()))
@@ -226,6 +243,28 @@ class PSALM:
                 getattr(static_plan, n).copy_(t, non_blocking=True)
         g.replay()
         return static_out
+
+    # ---- input staging: overlap the upload of batch k+1 with the compute of batch k ----------------------
+    def stage_images(self, images_host):
+        """Enqueue the host->device copy of a (pinned) image batch on a dedicated copy stream and return a
+        `StagedImages` handle for `eval_seg`.  Two device buffers per (shape, dtype) alternate; a buffer is reused
+        only after the pass that consumed it has read it (event recorded by eval_seg)."""
+        if not hasattr(self, "_stage"):
+            self._stage = dict(stream=torch.cuda.Stream(device=self.device), rings={}, count={})
+        st = self._stage
+        key = (tuple(images_host.shape), images_host.dtype)
+        ring = st["rings"].setdefault(key, [[torch.empty(images_host.shape, dtype=images_host.dtype, device=self.device),
+                                             None] for _ in range(2)])
+        n = st["count"].get(key, 0)
+        st["count"][key] = n + 1
+        slot = ring[n % 2]
+        with torch.cuda.stream(st["stream"]):
+            if slot[1] is not None:
+                st["stream"].wait_event(slot[1])
+            slot[0].copy_(images_host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(st["stream"])
+        return StagedImages(slot, ready)
 
     def make_plan(self, input_ids, attention_mask, image_hw, class_name_ids=None, cls_indices=None,
                   class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None):
@@ -271,7 +310,14 @@ class PSALM:
         if self.panoptic_on:
             assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
             self.is_thing_list = is_thing_list
-        images_d = images.to(self.device, non_blocking=True)
+        staged = images if isinstance(images, StagedImages) else None
+        if staged is not None:   # upload already in flight on the copy stream (stage_images)
+            torch.cuda.current_stream(self.device).wait_event(staged.ready)
+            images_d = staged.tensor
+        else:
+            # float images are the reference contract (already normalised by the mapper); uint8 images are raw pixel
+            # values, normalised on the device (coco_panoptic_mapper.py:161) - 4x fewer bytes over PCIe
+            images_d = images.to(self.device, non_blocking=True)
         plan = self._cached_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
                                  class_name_embedding_indices, token_refer_id, refer_embedding_indices)
         fused, boxes = self._fused_applies(images.shape[-2:], seg_info)
@@ -279,6 +325,9 @@ class PSALM:
             out = self.forward_core_graphed(images_d, plan, fuse_post=fused)
         else:
             out = self.forward_core(images_d, plan)
+        if staged is not None:   # the staging buffer may be overwritten once this pass has read it
+            staged.slot[1] = torch.cuda.Event()
+            staged.slot[1].record(torch.cuda.current_stream(self.device))
         return self.post_process(out, images.shape[-2:], seg_info, boxes)
 
     def _fused_applies(self, image_hw, seg_info):
@@ -317,7 +366,7 @@ class PSALM:
             trivial = (oh, ow) == (Hp, Wp) and (height, width) == (Hp, Wp)
             if trivial and out.get("post") is not None:
                 results.append(PP.fused_host(out["post"][b], getattr(self, "is_thing_list", None),
-                                             self.cfg.mask.overlap_threshold))
+                                             self.overlap_threshold))
                 continue
             if self.fused_postprocess and trivial and Hp >= 2 * H4 and Wp >= 2 * W4 and Q <= 104 and \
                     (cls_b is None or cls_b.shape[-1] - 1 <= 144):
@@ -325,7 +374,7 @@ class PSALM:
                 results.append(PP.fused_postprocess(
                     kernels, pm[b], Hp, Wp, cls_b, seg_b, getattr(self, "is_thing_list", None), self.semantic_on,
                     self.instance_on, self.panoptic_on, self.referring_on, self.test_topk_per_image,
-                    self.cfg.mask.object_mask_threshold, self.cfg.mask.overlap_threshold))
+                    self.object_mask_threshold, self.overlap_threshold))
                 continue
             if mask_pred is None:
                 mask_pred = F.interpolate(pm.float(), size=(Hp, Wp), mode="bilinear", align_corners=False)
@@ -347,8 +396,8 @@ class PSALM:
                                                        getattr(self, "is_thing_list", None), self.panoptic_on, sig)
             if self.panoptic_on:
                 r["panoptic_seg"] = PP.panoptic_inference(cls, mp, self.is_thing_list,
-                                                          self.cfg.mask.object_mask_threshold,
-                                                          self.cfg.mask.overlap_threshold, sig)
+                                                          self.object_mask_threshold,
+                                                          self.overlap_threshold, sig)
             if self.referring_on:
                 r["instances"] = PP.seg_instance_inference(out["pred_SEG_logits"][b].float(), mp,
                                                            self.test_topk_per_image, sig)

@@ -35,11 +35,14 @@ class SwinTransformer:
     def __init__(self, sd, prefix="model.vision_tower.", cfg=SwinConfig(), dtype=torch.bfloat16, device="cuda"):
         self.cfg, self.dtype, self.device = cfg, dtype, device
         self.image_processor = {}
+        # pixel statistics of the reference's dataset mappers (datasets_mapper/coco_panoptic_mapper.py:118-119):
+        # uint8 images are normalised on the device with them
+        self.pixel_mean = torch.tensor([123.675, 116.28, 103.53], dtype=torch.float32, device=device)
+        self.pixel_std = torch.tensor([58.395, 57.12, 57.375], dtype=torch.float32, device=device)
         self.num_features = [cfg.embed_dim * 2 ** i for i in range(len(cfg.depths))]
         g = lambda k: sd[prefix + k]  # noqa: E731
         cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
         w = {}
-        w["pe.w"] = cv(g("patch_embed.proj.weight")).contiguous(memory_format=torch.channels_last)
         w["pe.w2"] = cv(g("patch_embed.proj.weight").reshape(g("patch_embed.proj.weight").shape[0], -1))   # [C, 3*ps*ps]
         w["pe.b"] = cv(g("patch_embed.proj.bias"))
         w["pe.nw"], w["pe.nb"] = cv(g("patch_embed.norm.weight")), cv(g("patch_embed.norm.bias"))
@@ -78,26 +81,16 @@ class SwinTransformer:
     # -- token-major pipeline ----------------------------------------------------------------------
     def forward_tokens(self, images):
         cfg, w = self.cfg, self.w
-        _, Cin, H, W = images.shape
+        H, W = images.shape[-2:]
         ps = cfg.patch
-        if H % ps == 0 and W % ps == 0:
-            # non-overlapping ps x ps patches: the stride-ps convolution (swin_trans.py:427-441) is a GEMM over
-            # unfolded patches.  One strided copy does the unfold and the cast; bias rides in the GEMM epilogue
-            # (cuDNN's conv would add it in a separate broadcast pass).
-            B, Wh, Ww = images.shape[0], H // ps, W // ps
-            src = images.to(device=self.device).view(B, Cin, Wh, ps, Ww, ps).permute(0, 2, 4, 1, 3, 5)
-            patches = torch.empty((B, Wh, Ww, Cin, ps, ps), dtype=self.dtype, device=self.device)
-            patches.copy_(src)
-            x = F.linear(patches.view(B, Wh * Ww, Cin * ps * ps), w["pe.w2"], w["pe.b"])
-        else:
-            x = images.to(device=self.device, dtype=self.dtype)
-            if W % ps != 0:  # swin_trans.py:431-434
-                x = F.pad(x, (0, ps - W % ps))
-            if H % ps != 0:
-                x = F.pad(x, (0, 0, 0, ps - H % ps))
-            x = F.conv2d(x.contiguous(memory_format=torch.channels_last), w["pe.w"], w["pe.b"], stride=ps)
-            B, C, Wh, Ww = x.shape
-            x = x.permute(0, 2, 3, 1).reshape(B, Wh * Ww, C)
+        # One kernel: (uint8 input) pixel normalisation of the mapper (coco_panoptic_mapper.py:161), zero padding to
+        # the patch grid (swin_trans.py:431-434) and the unfold of the stride-ps convolution (:427-441), which is
+        # then a GEMM over the unfolded patches with the bias in its epilogue.
+        img = images.to(device=self.device).contiguous()
+        norm = (self.pixel_mean, self.pixel_std) if img.dtype == torch.uint8 else (None, None)
+        patches, (Wh, Ww) = kernels.patchify(img, self.dtype, norm[0], norm[1], ps)
+        B = img.shape[0]
+        x = F.linear(patches, w["pe.w2"], w["pe.b"])
         C = x.shape[-1]
         x = kernels.add_layer_norm(x.contiguous(), w["pe.nw"], w["pe.nb"])
         outs, sizes = [], []

@@ -132,10 +132,21 @@ def mask_bits(mask_embed, feats):
     return attn_mask_bits(mask_logits(mask_embed, feats, torch.float32))
 
 
+def patchify(images, out_dtype, mean=None, std=None, patch=4):
+    x = images.float()
+    if mean is not None:
+        x = (x - mean.view(1, -1, 1, 1)) / std.view(1, -1, 1, 1)
+    B, C, H, W = x.shape
+    x = F.pad(x, (0, (-W) % patch, 0, (-H) % patch))
+    Wh, Ww = x.shape[2] // patch, x.shape[3] // patch
+    x = x.view(B, C, Wh, patch, Ww, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, Wh * Ww, C * patch * patch)
+    return x.to(out_dtype), (Wh, Ww)
+
+
 def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
-                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits"):
+                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify"):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 

@@ -32,7 +32,19 @@ def _worker(rank, world, port, out_q):
         recs.append(PD.compact_record({"instances": inst}, num_queries=10))
     allr = PD.gather_records(torch.stack(recs))
     mx = PD.max_over_ranks([float(rank + 1), 5.0 - rank], "cpu")
-    out_q.put((rank, mine, allr[:, 0, 0].tolist(), allr.shape, mx))
+    # per-step prediction gather (class / score + panoptic id maps) and metric-accumulator reduction
+    res = []
+    for i in range(2):
+        inst = Instances((4, 6))
+        inst.scores = torch.full((3,), float(rank) + 0.5)
+        inst.pred_classes = torch.tensor([1, 2, 3]) + 10 * rank
+        res.append({"instances": inst, "panoptic_seg": (torch.full((4, 6), 7 * rank + i, dtype=torch.int32), [])})
+    meta, maps = PD.pack_predictions(res, num_queries=5)
+    gmeta, gmaps = PD.gather_predictions(meta, maps)
+    acc = PD.reduce_sum([torch.tensor([1.0, float(rank)]), torch.ones(2, 2, dtype=torch.int64)], "cpu")
+    extra = (tuple(gmeta.shape), gmeta[:, 0, 1].tolist(), gmeta[:, 4, 1].tolist(), gmaps[:, 0, 0].tolist(),
+             acc[0].tolist(), acc[1].sum().item())
+    out_q.put((rank, mine, allr[:, 0, 0].tolist(), allr.shape, mx, extra))
     dist.destroy_process_group()
 
 
@@ -53,6 +65,9 @@ def test_two_rank_gloo_shard_gather_reduce():
         assert r[2] == [0.0, 1.0, 2.0, 10.0, 11.0, 12.0]      # rank order preserved
         assert tuple(r[3]) == (6, 10, 3)
         assert r[4] == [2.0, 5.0]                               # max over ranks
+        shape, cls0, cls4, map00, acc0, acc1 = r[5]
+        assert shape == (4, 5, 2) and cls0 == [1.0, 1.0, 11.0, 11.0] and cls4 == [-1.0] * 4   # empty slots = -1
+        assert map00 == [0, 1, 7, 8] and acc0 == [2.0, 1.0] and acc1 == 8
 
 
 def test_single_process_passthrough():

@@ -166,3 +166,98 @@ def test_errors_are_loud():
         msda.ms_deform_attn_forward(v, [(3, 3)], [0], loc, w)
     with pytest.raises(RuntimeError, match="contiguous"):
         msda.ms_deform_attn_forward(v.expand(2, 4, 1, 4)[:, ::2], [(2, 1)], [0], loc, w)
+
+
+def _reference_cuda_op():
+    """The reference's OWN CUDA extension built for sm_100 by baseline/build_ref_msda.py (build container only;
+    the .so travels to the GPU box, its sources do not enter the repository)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "baseline", "_ref", "MultiScaleDeformableAttention.so")
+    if not os.path.exists(so):
+        pytest.skip("baseline/_ref not built (python baseline/build_ref_msda.py in the build container)")
+    spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttention", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16"])
+def test_against_the_reference_cuda_kernel(dt):
+    """Same operands into the reference's ms_deform_attn_forward (ms_deformable_im2col_gpu_kernel) and ours, at the
+    1024^2 encoder geometry: the two kernels must agree to accumulation-order noise."""
+    refop = _reference_cuda_op()
+    torch.manual_seed(7)
+    shapes = [(32, 32), (64, 64), (128, 128)]
+    st = _starts(shapes)
+    S, M, D, L, P = sum(h * w for h, w in shapes), 8, 32, 3, 4
+    B = 2
+    dev = "cuda"
+    v = torch.randn(B, S, M, D, device=dev).to(DT[dt])
+    loc = (torch.rand(B, S, M, L, P, 2, device=dev) * 1.2 - 0.1).to(DT[dt])
+    aw = torch.softmax(torch.randn(B, S, M, L * P, device=dev), -1).view(B, S, M, L, P).to(DT[dt])
+    sh_t = torch.tensor(shapes, dtype=torch.long, device=dev)
+    st_t = torch.tensor(st, dtype=torch.long, device=dev)
+    theirs = refop.ms_deform_attn_forward(v, sh_t, st_t, loc, aw, 128)
+    ours = msda.ms_deform_attn_forward(v, sh_t, st_t, loc, aw, 128)
+    torch.cuda.synchronize()
+    assert ours.shape == theirs.shape and ours.dtype == theirs.dtype
+    err = (ours.double() - theirs.double()).abs().max() / theirs.double().abs().max()
+    # fp32: both accumulate in fp32 (different order); fp16: the reference accumulates in HALF, we in fp32
+    assert err < (2e-6 if dt == "f32" else 5e-3), err
+
+
+def test_compat_module_runs_the_reference_autograd_function():
+    """`import MultiScaleDeformableAttention` (the pybind module name the reference imports,
+    ops/functions/ms_deform_attn_func.py:21-29) resolves to psalm_b200/compat, and a restated
+    MSDeformAttnFunction.forward (func.py:34-39) runs on it unmodified; backward raises (inference build)."""
+    import importlib
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "psalm_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        sys.modules.pop("MultiScaleDeformableAttention", None)
+        MSDA = importlib.import_module("MultiScaleDeformableAttention")
+    finally:
+        sys.path.remove(compat)
+
+    class MSDeformAttnFunction(torch.autograd.Function):   # restated from func.py:32-39
+        @staticmethod
+        def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                    im2col_step):
+            ctx.im2col_step = im2col_step
+            output = MSDA.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                                 sampling_locations, attention_weights, ctx.im2col_step)
+            ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                  attention_weights)
+            return output
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msda_m8d32.npz"))
+    dev = "cuda"
+    shapes = torch.from_numpy(g["shapes"]).long().to(dev)
+    starts = torch.tensor(_starts(g["shapes"]), dtype=torch.long, device=dev)
+    out = MSDeformAttnFunction.apply(torch.from_numpy(g["value"]).to(dev), shapes, starts,
+                                     torch.from_numpy(g["loc"]).to(dev), torch.from_numpy(g["aw"]).to(dev), 128)
+    torch.cuda.synchronize()
+    assert np.allclose(out.cpu().numpy(), g["out_f32"], rtol=1e-2, atol=1e-3)     # the reference's own tolerance
+    assert np.allclose(out.cpu().numpy(), g["out_f64"], rtol=1e-4, atol=1e-8)
+    with pytest.raises(NotImplementedError):
+        MSDA.ms_deform_attn_backward()
+
+
+def test_output_is_fully_overwritten():
+    """The reference zero-initialises its output (ms_deform_attn_cuda.cu:59); ours allocates with torch.empty, so
+    every element must be written by the kernel: poison the allocator's next block first."""
+    torch.manual_seed(3)
+    shapes = [(5, 7), (3, 4)]
+    S, M, D, L, P = 47, 2, 32, 2, 3
+    v = torch.randn(1, S, M, D, device="cuda")
+    loc = torch.rand(1, S, M, L, P, 2, device="cuda") * 3 - 1      # many samples fall outside (zero contribution)
+    aw = torch.softmax(torch.randn(1, S, M, L * P, device="cuda"), -1).view(1, S, M, L, P)
+    for _ in range(3):
+        poison = torch.full((1, S, M * D), float("nan"), device="cuda")
+        del poison                                                   # same size: the next empty() reuses this block
+        out = msda.ms_deform_attn_forward(v, shapes, _starts(shapes), loc, aw, 128)
+        assert torch.isfinite(out).all()

@@ -29,7 +29,20 @@ def timeit(fn, iters=20, warmup=5, flush=None):
     return ts[len(ts) // 2], ts[0]
 
 
+def load_reference_op():
+    """The reference's own CUDA op built for sm_100 by baseline/build_ref_msda.py (None if it was not built)."""
+    import importlib.util
+    so = os.path.join(ROOT, "baseline", "_ref", "MultiScaleDeformableAttention.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttention", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def main():
+    refop = load_reference_op()
     peaks = {}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -60,9 +73,19 @@ def main():
                 med, best = timeit(lambda: msda.ms_deform_attn_forward(vv, shapes, st, loc, aw, 128, value_layout=lay), flush=flush)
                 key = "%s_layout%d_spread%g" % (name, lay, spread)
                 res[key] = dict(us=med, best_us=best, gbs=bytes_boundary / med / 1e3, frac=bytes_boundary / med / 1e3 / hbm)
+            sh_t = torch.tensor(shapes, dtype=torch.long, device=dev)
+            st_t = torch.tensor(st, dtype=torch.long, device=dev)
+            if refop is not None and dt != torch.bfloat16:   # the reference dispatches float / double / half only
+                # the kernel to beat: ms_deformable_im2col_gpu_kernel at ITS boundary (loc / w in value's dtype)
+                locr, awr = loc.to(dt), aw.to(dt)
+                bytes_ref = B * (es * S * M * D * 2 + es * S * M * L * P * 3)
+                med, best = timeit(lambda: refop.ms_deform_attn_forward(v, sh_t, st_t, locr, awr, 128), flush=flush)
+                res["%s_REFERENCE_kernel_spread%g" % (name, spread)] = dict(us=med, best_us=best, gbs=bytes_ref / med / 1e3,
+                                                                            frac=bytes_ref / med / 1e3 / hbm)
+                ours = msda.ms_deform_attn_forward(v, sh_t, st_t, locr, awr, 128)
+                theirs = refop.ms_deform_attn_forward(v, sh_t, st_t, locr, awr, 128)
+                res["%s_REFERENCE_kernel_spread%g" % (name, spread)]["max_abs_diff_vs_ours"] = float((ours.float() - theirs.float()).abs().max())
             if lay == 1:
-                sh_t = torch.tensor(shapes, dtype=torch.long, device=dev)
-                st_t = torch.tensor(st, dtype=torch.long, device=dev)
                 med, best = timeit(lambda: msda.ms_deform_attn_forward(v, sh_t, st_t, loc, aw, 128), flush=flush)
                 res["%s_devshapes_linear_spread%g" % (name, spread)] = dict(us=med, best_us=best, gbs=bytes_boundary / med / 1e3)
             # fused: ow in the value dtype and in fp32
