@@ -165,10 +165,11 @@ def bench_inputs(batch, seed):
     in fp32 exactly like the mapper (coco_panoptic_mapper.py:161)."""
     from psalm_b200 import synth
     inp = synth.synth_inputs(batch=batch, height=IMG, width=IMG, task="panoptic", n_classes=N_CLASSES, seed=seed)
-    g = torch.Generator().manual_seed(1000 + seed)
-    u8 = torch.randint(0, 256, (batch, 3, IMG, IMG), generator=g, dtype=torch.uint8)
     mean = torch.tensor(PIXEL_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(PIXEL_STD).view(1, 3, 1, 1)
+    # uint8 pixels with the statistics the mapper's normalisation expects: the N(0, 1) synthetic image, de-normalised,
+    # rounded and clamped to [0, 255]
+    u8 = (inp["images"] * std + mean).round().clamp(0, 255).to(torch.uint8)
     inp["images_u8"] = u8
     inp["images"] = (u8 - mean) / std
     return inp
@@ -402,8 +403,14 @@ def run_ours(args, rank, world, local_rank):
                 one = {k: (v[:1] if torch.is_tensor(v) else v) for k, v in out_timed.items()}
                 parity_line = {"bf16_graph_path": dict(parity.final_metrics(one, it),
                                                        **parity.result_metrics(res_relaxed[:1], ores, "panoptic")),
+                               "bf16_stages_teacher_forced_l2rel": parity.forced_stage_errors(model, it, inp["images"][:1]),
+                               "bf16_decoder_layers_teacher_forced": parity.forced_layer_errors(model, it),
+                               "oracle_decoder_sensitivity_to_bf16_inputs": parity.predictor_sensitivity(sd, it, torch.bfloat16),
                                "note": "image 0 of the timed batch vs the CPU oracle on the same bf16-rounded weights; task "
-                                       "outputs compared at panoptic thresholds 0.0 / 0.0 in both arms"}
+                                       "outputs compared at panoptic thresholds 0.0 / 0.0 in both arms; teacher-forced = every "
+                                       "stage / decoder layer fed the oracle's inputs; sensitivity = the ORACLE's decoder "
+                                       "re-run on its own inputs rounded to bf16 (the masked attention thresholds mask "
+                                       "logits: a discontinuity of the reference itself)"}
             r, o = res_relaxed[b], ores[0]
             acc.add_panoptic(r["panoptic_seg"][0].cpu().numpy(), r["panoptic_seg"][1], o["panoptic_seg"][0].numpy(),
                              o["panoptic_seg"][1])

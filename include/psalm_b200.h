@@ -194,6 +194,26 @@ int psalm_postproc_fused(const void* logits, const void* probsT_f16, const float
                          int K, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Masked cross-attention of the Mask2Former decoder, all 8 heads of a key range per CTA, K/V through TMA
+ * (csrc/xattn_tma.cu).  Same mathematics as psalm_cross_attention; replaces CrossAttentionLayer.forward_post's
+ * nn.MultiheadAttention call (transformer_decoder/mask2former_transformer_decoder.py:93-105) for 16-bit storage.
+ *   q        [B,Lq,256]  projected queries (8 heads x 32), Lq <= 112
+ *   k, v     [B,Lk,256]  projected keys / values as ROW-STRIDED views: row n of image b starts at
+ *            base + (b*Lk + n) * kv_row_stride elements (kv_row_stride = 256 for separate contiguous tensors, 768
+ *            when the K (or V) projections of the three decoder layers sharing a feature level are one GEMM)
+ *   mask_bits [B,Lq,ceil(Lk/32)] bit j of word w = key 32w+j BLOCKED (shared by the heads), or NULL
+ *   row_open  [B,Lq] != 0: ignore the mask for that row (fully blocked rows attend everywhere, :647), or NULL
+ *   workspace: psalm_masked_cross_attention_workspace_bytes(B, Lq, Lk) bytes (split-K partials), may be NULL if 0
+ * ------------------------------------------------------------------------------------------ */
+/* implementation selector: 0 = auto (tcgen05 + TMEM kernel, csrc/xattn_tc5.cu), 1 = warp-level mma.sync kernel
+ * (csrc/xattn_tma.cu), 2 = tcgen05.  Both are fed by TMA. */
+int psalm_set_cross_impl(int impl);
+size_t psalm_masked_cross_attention_workspace_bytes(int B, int Lq, int Lk);
+int psalm_masked_cross_attention(const void* q, const void* k, const void* v, long long kv_row_stride,
+                                 const uint32_t* mask_bits, const uint8_t* row_open, void* out, float* workspace,
+                                 size_t workspace_bytes, int B, int Lq, int Lk, int nh, int hd, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Input pipeline on the device: pixel normalisation + zero padding to the patch grid +
  * unfold into the operand of the patch-embedding GEMM, one pass.
  * Replaces: `(image - pixel_mean) / pixel_std` on the host (datasets_mapper/coco_panoptic_mapper.py:161; the

@@ -136,5 +136,96 @@ def forced_stage_errors(model, it, images):
     return e
 
 
+def pack_mask(blocked):
+    """bool [B,Q,P] (True = blocked) -> (bits int32 [B,Q,ceil(P/32)], row_open uint8 [B,Q]) in the kernels' format."""
+    B, Q, P = blocked.shape
+    W32 = (P + 31) // 32
+    w = torch.zeros(B, Q, W32 * 32, dtype=torch.int64)
+    w[..., :P] = blocked.long()
+    words = (w.view(B, Q, W32, 32) << torch.arange(32)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    return words, blocked.all(-1).to(torch.uint8)
+
+
+class _LayerTeacher:
+    """Layer-wise teacher forcing of the masked decoder: every layer starts from the ORACLE's decoder state and the
+    ORACLE's attention mask, so the error of a layer's output is that layer's kernels + storage rounding only; the
+    mask-prediction kernels are scored separately as the bit agreement of the mask they derive from the oracle's
+    state.  (End to end, one flipped mask bit changes which keys a query attends to - a discontinuity the reference
+    has too, see `predictor_sensitivity`.)"""
+
+    def __init__(self, model, it, nh=8):
+        self.m, self.po = model, it["predictor"]
+        self.sizes = [tuple(t.shape[-2:]) for t in it["ms"]]
+        self.nh = nh
+        self.layer_l2, self.mask_agree, self.mask_agree_off_threshold = [], [], []
+
+    def _g(self, t):
+        return t.to(device=self.m.device, dtype=self.m.dtype)
+
+    def before_layer(self, i, output, bits, row_open, mask_for):
+        state = self._g(self.po["layer_outputs"][i].permute(1, 0, 2).contiguous())      # [B,Q,C]
+        ref_mask = self.po["trace"][i][3]                                               # bool [B*nh, Q, HW], heads identical
+        B = state.shape[0]
+        blocked = ref_mask.view(B, self.nh, ref_mask.shape[1], ref_mask.shape[2])[:, 0]
+        rb, ro = pack_mask(blocked)
+        # mask-prediction kernels on the oracle's state
+        pb, _ = mask_for(state)
+        flips = (pb.cpu() ^ rb)
+        nbits = blocked.numel()
+        nflip = sum(int(((flips >> k) & 1).sum()) for k in range(32))
+        self.mask_agree.append(1.0 - nflip / nbits)
+        # flips away from the decision threshold (|oracle mask logit| at the target size > 1e-2 of its rms)
+        lg = torch.nn.functional.interpolate(self.po["trace"][i][2].float(), size=self.sizes[i % 3], mode="bilinear",
+                                             align_corners=False).flatten(2)
+        hw = blocked.shape[-1]
+        firm = lg.abs() > 1e-2 * lg.pow(2).mean().sqrt()
+        bit = torch.stack([((flips >> k) & 1) for k in range(32)], -1).view(B, blocked.shape[1], -1)[..., :hw].bool()
+        self.mask_agree_off_threshold.append(1.0 - float((bit & firm).sum()) / max(1, int(firm.sum())))
+        return state, rb.to(self.m.device), ro.to(self.m.device)
+
+    def after_layer(self, i, output):
+        ref = self.po["layer_outputs"][i + 1].permute(1, 0, 2)
+        self.layer_l2.append(_l2rel(output.float().cpu(), ref))
+
+
+def forced_layer_errors(model, it):
+    """Per decoder layer: l2-relative error of the layer output and mask-bit agreement, layer-wise teacher forced."""
+    dev, dt = model.device, model.dtype
+    g = lambda t: t.to(device=dev, dtype=dt)  # noqa: E731
+    teacher = _LayerTeacher(model, it)
+    pred = model.predictor
+    ms = [g(_tok(t)).contiguous() for t in it["ms"]]
+    sizes = [tuple(t.shape[-2:]) for t in it["ms"]]
+    mf = g(_tok(it["mask_features"])).contiguous()
+    with torch.no_grad(), model._precision_scope():
+        pred.forward_tokens(ms, sizes, mf, tuple(it["mask_features"].shape[-2:]), g(it["seg_query"]),
+                            g(it["SEG_emb"]) if it.get("SEG_emb") is not None else None,
+                            g(it["cls_emb"]) if it.get("cls_emb") is not None else None, hooks=teacher)
+    e = {"layer_l2rel_max": max(teacher.layer_l2), "layer_l2rel": [round(x, 5) for x in teacher.layer_l2],
+         "mask_bit_agree_min": min(teacher.mask_agree)}
+    if teacher.mask_agree_off_threshold:
+        e["mask_bit_agree_off_threshold_min"] = min(teacher.mask_agree_off_threshold)
+    return e
+
+
+def predictor_sensitivity(sd, it, dtype):
+    """Conditioning of the REFERENCE function itself: the oracle's masked decoder re-run (CPU, fp32 arithmetic) on its
+    own inputs rounded once to `dtype`, against the un-rounded run.  Thresholded attention masks make the decoder
+    discontinuous; on random weights many mask logits sit at the threshold, so a 2^-9 input perturbation can move the
+    output by tens of percent.  A GPU run in 16-bit storage cannot be closer to the fp32 oracle than this."""
+    from oracle import psalm_oracle as O
+    r = lambda t: None if t is None else t.to(dtype).float()  # noqa: E731
+    with torch.no_grad():
+        po = O.predictor_forward(sd, "predictor.", [r(t) for t in it["ms"]], r(it["mask_features"]), r(it["seg_query"]),
+                                 r(it.get("SEG_emb")), r(it.get("cls_emb")))
+    ref = it["predictor"]
+    e = {"pred_masks_l2rel": _l2rel(po["pred_masks"], ref["pred_masks"]), "pred_masks_maxrel": _maxrel(po["pred_masks"], ref["pred_masks"]),
+         "mask_sign_agree": float(((po["pred_masks"] > 0) == (ref["pred_masks"] > 0)).double().mean())}
+    if ref.get("pred_class_name_logits") is not None:
+        e["class_logits_l2rel"] = _l2rel(po["pred_class_name_logits"], ref["pred_class_name_logits"])
+    return e
+
+
 def fmt(d):
     return ", ".join("%s %s" % (k, ("%.3e" % v) if isinstance(v, float) else v) for k, v in d.items())

@@ -479,6 +479,7 @@ def predictor_forward(sd, pre, ms_feats, mask_features, seg_query, SEG_embedding
     SEGc, clsc, omask, attn_mask = prediction_heads(sd, pre, output, mask_features, sizes[0], SEG_embedding,
                                                     class_name_embedding, nh)
     trace = [(SEGc, clsc, omask, attn_mask)]
+    layer_outputs = [output]        # decoder state before layer 0, then after every layer ([Q, B, C])
     n_layers = 0
     while "%stransformer_ffn_layers.%d.norm.weight" % (pre, n_layers) in sd:
         n_layers += 1
@@ -499,9 +500,11 @@ def predictor_forward(sd, pre, ms_feats, mask_features, seg_query, SEG_embedding
         SEGc, clsc, omask, attn_mask = prediction_heads(sd, pre, output, mask_features, sizes[(i + 1) % 3],
                                                         SEG_embedding, class_name_embedding, nh)
         trace.append((SEGc, clsc, omask, attn_mask))
+        layer_outputs.append(output)
     out = dict(pred_SEG_logits=SEGc, pred_class_name_logits=clsc, pred_masks=omask)
     if return_all:
         out["trace"] = trace
+        out["layer_outputs"] = layer_outputs
     return out
 
 

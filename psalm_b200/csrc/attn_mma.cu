@@ -108,13 +108,13 @@ struct CrossMma {
   const uint8_t* row_open;
   T* out;
   int Lq, Lk, nh, hd, W32;
+  int kv_ld;   // elements between consecutive K (and V) rows: nh * hd, or more for views of a fused projection buffer
   static constexpr bool kCausal = false;
   __device__ __forceinline__ const T* ptr(int which, int b, int h, int n, int d0) const {
-    const T* base = which == 0 ? q : (which == 1 ? k : v);
-    const int L = which == 0 ? Lq : Lk;
-    return base + ((size_t)b * L + n) * nh * hd + h * hd + d0;
+    if (which == 0) return q + ((size_t)b * Lq + n) * nh * hd + h * hd + d0;
+    return (which == 1 ? k : v) + ((size_t)b * Lk + n) * kv_ld + h * hd + d0;
   }
-  __device__ __forceinline__ size_t row_stride() const { return (size_t)nh * hd; }
+  __device__ __forceinline__ size_t row_stride() const { return (size_t)kv_ld; }
   __device__ __forceinline__ uint4 load8(int which, int b, int h, int n, int d0) const {
     return ldg16(ptr(which, b, h, n, d0));
   }
@@ -758,15 +758,16 @@ int mma_causal_attention(const void* qkv, const uint8_t* key_valid, void* out, i
 
 int mma_cross_attention(const void* q, const void* k, const void* v, const uint32_t* bits, const uint8_t* row_open,
                         void* out, float* workspace, int B, int Lq, int Lk, int nh, int hd, int splits, int dtype,
-                        cudaStream_t st) {
+                        cudaStream_t st, int kv_ld) {
+  if (kv_ld <= 0) kv_ld = nh * hd;
   AttnDims dm{B, nh, Lq, Lk, splits, 1.0f / sqrtf((float)hd)};
   if (dtype == PSALM_BF16) {
     using T = __nv_bfloat16;
-    CrossMma<T> pol{(const T*)q, (const T*)k, (const T*)v, bits, row_open, (T*)out, Lq, Lk, nh, hd, (Lk + 31) / 32};
+    CrossMma<T> pol{(const T*)q, (const T*)k, (const T*)v, bits, row_open, (T*)out, Lq, Lk, nh, hd, (Lk + 31) / 32, kv_ld};
     return launch_flash<T>(pol, dm, hd, workspace, st, "cross_attention(mma)");
   }
   using T = __half;
-  CrossMma<T> pol{(const T*)q, (const T*)k, (const T*)v, bits, row_open, (T*)out, Lq, Lk, nh, hd, (Lk + 31) / 32};
+  CrossMma<T> pol{(const T*)q, (const T*)k, (const T*)v, bits, row_open, (T*)out, Lq, Lk, nh, hd, (Lk + 31) / 32, kv_ld};
   return launch_flash<T>(pol, dm, hd, workspace, st, "cross_attention(mma)");
 }
 

@@ -326,7 +326,7 @@ namespace psalm {
 // tensor-core paths (attn_mma.cu)
 int mma_causal_attention(const void*, const uint8_t*, void*, int, int, int, int, int, cudaStream_t);
 int mma_cross_attention(const void*, const void*, const void*, const uint32_t*, const uint8_t*, void*, float*, int,
-                        int, int, int, int, int, int, cudaStream_t);
+                        int, int, int, int, int, int, cudaStream_t, int kv_ld = 0);
 int mma_window_attention(const void*, const void*, const float*, void*, int, int, int, int, int, int, int,
                          cudaStream_t);
 extern int g_splitk_mode;

@@ -319,3 +319,31 @@ def patchify(images, out_dtype, mean=None, std=None, patch=4):
     _lib.check(rc, "psalm_patchify")
     _count()
     return out, (Wh, Ww)
+
+
+@_on_device
+def masked_cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, workspace=None):
+    """q [B,Lq,256]; k, v [B,Lk,256] possibly ROW-STRIDED views (last dim contiguous, batch stride = Lk * row stride)
+    -> [B,Lq,256].  TMA-fed kernel of csrc/xattn_tma.cu (16-bit storage, 8 heads x 32)."""
+    _chk(q, "masked_cross_attention.q")
+    B, Lq, C = q.shape
+    Lk = k.shape[1]
+    ld = k.stride(1)
+    for t, n in ((k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != q.dtype or tuple(t.shape) != (B, Lk, C) or t.stride(2) != 1 or t.stride(1) != ld or \
+                (B > 1 and t.stride(0) != Lk * ld):
+            raise _lib.PsalmKernelError("masked_cross_attention.%s: expected a [B,Lk,%d] view with contiguous rows and a "
+                                        "common row stride" % (n, C))
+    L = _lib.lib()
+    need = L.psalm_masked_cross_attention_workspace_bytes(B, Lq, Lk)
+    if need and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty(need // 4, dtype=torch.float32, device=q.device)
+    out = torch.empty_like(q)
+    rc = L.psalm_masked_cross_attention(
+        _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), ld, _lib.ptr(mask_bits) if mask_bits is not None else None,
+        _lib.ptr(row_open) if row_open is not None else None, _lib.ptr(out),
+        _lib.ptr(workspace) if need else None, workspace.numel() * workspace.element_size() if need else 0,
+        B, Lq, Lk, nh, C // nh, _lib.dtype_code(q.dtype), _lib.stream_ptr(q.device))
+    _lib.check(rc, "psalm_masked_cross_attention")
+    _count(2 if need else 1)
+    return out

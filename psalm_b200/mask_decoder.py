@@ -41,6 +41,13 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             p = "transformer_ffn_layers.%d." % i
             for n in ("linear1", "linear2", "norm"):
                 w["f%d.%s.w" % (i, n)], w["f%d.%s.b" % (i, n)] = cv(g(p + n + ".weight")), cv(g(p + n + ".bias"))
+        # K (and V) projections of the decoder layers that share a feature level (layers li, li+3, li+6 read the same
+        # memory, :642-650) as ONE weight matrix per level: 2 x 3 GEMMs per image instead of 2 x 9
+        for li in range(3):
+            layers = list(range(li, cfg.dec_layers, 3))
+            for n in "kv":
+                w["x%s_all%d.w" % (n, li)] = torch.cat([w["x%d.%s.w" % (i, n)] for i in layers], 0).contiguous()
+                w["x%s_all%d.b" % (n, li)] = torch.cat([w["x%d.%s.b" % (i, n)] for i in layers], 0).contiguous()
         w["dn.w"], w["dn.b"] = cv(g("decoder_norm.weight")), cv(g("decoder_norm.bias"))
         self.query_embed = cv(g("query_embed.weight"))      # forward_woconcat uses query_embed (:619)
         self.level_embed = cv(g("level_embed.weight"))
@@ -78,9 +85,12 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
         return out
 
     def forward_tokens(self, ms_tokens, ms_sizes, mask_features, mf_size, seg_query, SEG_embedding=None,
-                       class_name_embedding=None, return_trace=False):
+                       class_name_embedding=None, return_trace=False, hooks=None):
         """ms_tokens: 3 maps [B,HW_l,256] (32^2,64^2,128^2 levels); mask_features [B,H4*W4,256];
-        seg_query [B,Q,256].  Returns dict(pred_masks [B,Q,H4*W4], pred_class_name_logits, pred_SEG_logits)."""
+        seg_query [B,Q,256].  Returns dict(pred_masks [B,Q,H4*W4], pred_class_name_logits, pred_SEG_logits).
+        `hooks` (tests only, oracle/parity.py): an object whose before_layer(i, output, bits, row_open, mask_for) may
+        substitute the decoder state / attention mask entering layer i (layer-wise teacher forcing) and whose
+        after_layer(i, output) observes the state leaving it."""
         cfg, w = self.cfg, self.w
         B, Q, Hd = seg_query.shape
         nh = cfg.nheads
@@ -104,14 +114,29 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
                 trace.append(kernels.mask_logits(me.contiguous(), pooled[level], out_dtype=torch.float32))
             return kernels.mask_bits(me.contiguous(), pooled[level])
 
+        # 16-bit storage: all K / V projections of a level up front (one GEMM each), consumed as row-strided views by
+        # the TMA-fed kernel; fp32 storage keeps the per-layer projections + the SIMT kernel
+        fused_kv = self.dtype != torch.float32 and Hd == 256 and nh == 8 and Q <= 112
+        if fused_kv:
+            k_all = [F.linear(kins[li], w["xk_all%d.w" % li], w["xk_all%d.b" % li]) for li in range(3)]
+            v_all = [F.linear(srcs[li], w["xv_all%d.w" % li], w["xv_all%d.b" % li]) for li in range(3)]
         bits, row_open = mask_for(0, output)
         for i in range(cfg.dec_layers):
             li = i % 3
+            if hooks is not None:
+                output, bits, row_open = hooks.before_layer(i, output, bits, row_open, lambda o_, lv=li: mask_for(lv, o_))
             # masked cross-attention (:93-105): q = tgt + query_pos, k = memory + pos, v = memory
             q = F.linear(output + qpos, w["x%d.q.w" % i], w["x%d.q.b" % i])
-            k = F.linear(kins[li], w["x%d.k.w" % i], w["x%d.k.b" % i])
-            v = F.linear(srcs[li], w["x%d.v.w" % i], w["x%d.v.b" % i])
-            a = kernels.timed("masked_cross_attention_%d" % k.shape[1], kernels.cross_attention, q, k, v, bits, row_open, nh)
+            if fused_kv:
+                j = i // 3
+                k, v = k_all[li][:, :, j * Hd:(j + 1) * Hd], v_all[li][:, :, j * Hd:(j + 1) * Hd]
+                a = kernels.timed("masked_cross_attention_%d" % k.shape[1], kernels.masked_cross_attention, q, k, v,
+                                  bits, row_open, nh)
+            else:
+                k = F.linear(kins[li], w["x%d.k.w" % i], w["x%d.k.b" % i])
+                v = F.linear(srcs[li], w["x%d.v.w" % i], w["x%d.v.b" % i])
+                a = kernels.timed("masked_cross_attention_%d" % k.shape[1], kernels.cross_attention, q, k, v, bits,
+                                  row_open, nh)
             output = kernels.add_layer_norm(output, w["x%d.n.w" % i], w["x%d.n.b" % i],
                                             r1=F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]))
             # query self-attention (:35-45): q = k = tgt + query_pos, v = tgt
@@ -126,6 +151,8 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             f = F.linear(kernels.linear_act(output, w["f%d.linear1.w" % i], w["f%d.linear1.b" % i], "relu"),
                          w["f%d.linear2.w" % i], w["f%d.linear2.b" % i])
             output = kernels.add_layer_norm(output, w["f%d.norm.w" % i], w["f%d.norm.b" % i], r1=f)
+            if hooks is not None:
+                hooks.after_layer(i, output)
             if i < cfg.dec_layers - 1:
                 bits, row_open = mask_for((i + 1) % 3, output)
         # final prediction heads (:695-750) — the only ones whose outputs leave the decoder

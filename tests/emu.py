@@ -71,6 +71,10 @@ def cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, splits=None, w
     return (s.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B, Lq, C).to(q.dtype)
 
 
+def masked_cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, workspace=None):
+    return cross_attention(q, k, v, mask_bits, row_open, nh)
+
+
 def mask_logits(mask_embed, feats, out_dtype=None):
     return torch.bmm(mask_embed.float(), feats.float().transpose(1, 2)).to(out_dtype or mask_embed.dtype)
 
@@ -146,7 +150,7 @@ def patchify(images, out_dtype, mean=None, std=None, patch=4):
 def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
-                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify"):
+                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify", "masked_cross_attention"):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 

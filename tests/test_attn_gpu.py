@@ -88,6 +88,50 @@ def test_cross_attention_with_bit_mask(dt, Lq, Lk, splits):
     _close(out2, ref2, dt)
 
 
+@pytest.mark.parametrize("impl", [0, 2, 1], ids=["auto", "tcgen05", "mma"])
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("B,Lq,Lk,ld", [(2, 100, 1024, 256), (4, 100, 4096, 768), (1, 100, 16384, 768), (4, 100, 16384, 256),
+                                        (2, 100, 27889, 768), (3, 37, 100, 256), (1, 112, 389, 768), (2, 1, 33, 256),
+                                        (5, 100, 6400, 768), (1, 100, 31, 256)])
+def test_masked_cross_attention_tma(impl, dt, B, Lq, Lk, ld):
+    """The TMA-fed masked cross-attention kernels (tcgen05 + TMEM: csrc/xattn_tc5.cu; warp-level mma.sync:
+    csrc/xattn_tma.cu) vs the torch restatement: packed bit masks, fully blocked rows that re-open, fully open rows,
+    ragged key counts (tail tile), row-strided K / V views of a fused projection buffer, single-CTA and split-K grids,
+    and the no-mask case."""
+    from psalm_b200 import _lib
+    _lib.check(_lib.lib().psalm_set_cross_impl(impl), "psalm_set_cross_impl")
+    try:
+        _masked_cross_attention_case(dt, B, Lq, Lk, ld)
+    finally:
+        _lib.lib().psalm_set_cross_impl(0)
+
+
+def _masked_cross_attention_case(dt, B, Lq, Lk, ld):
+    torch.manual_seed(B * 1000 + Lq + Lk)
+    nh, C = 8, 256
+    q = torch.randn(B, Lq, C).to(DT[dt])
+    kbuf, vbuf = torch.randn(B, Lk, ld).to(DT[dt]), torch.randn(B, Lk, ld).to(DT[dt])
+    off = 0 if ld == 256 else 256
+    logits = torch.randn(B, Lq, Lk)
+    # spatially structured masks: long blocked runs (whole 16 x 32 blocks get skipped) and noise elsewhere
+    logits[:, :, : Lk // 3] -= 4.0
+    logits[0, min(3, Lq - 1)] = -1.0          # fully blocked row -> must attend everywhere (DEC:647)
+    logits[B - 1, 0] = 1.0                     # fully open row
+    bits, row_open = emu.attn_mask_bits(logits)
+    kg, vg = kbuf.cuda(), vbuf.cuda()
+    k, v = kg[:, :, off:off + C], vg[:, :, off:off + C]
+    ref = emu.cross_attention(q.float(), kbuf[:, :, off:off + C].float(), vbuf[:, :, off:off + C].float(), bits, row_open, nh)
+    out = kernels.masked_cross_attention(q.cuda(), k, v, bits.cuda(), row_open.cuda(), nh)
+    torch.cuda.synchronize()
+    _close(out, ref, dt)
+    ref2 = emu.cross_attention(q.float(), kbuf[:, :, off:off + C].float(), vbuf[:, :, off:off + C].float(), None, None, nh)
+    out2 = kernels.masked_cross_attention(q.cuda(), k, v, None, None, nh)
+    _close(out2, ref2, dt)
+    # same answer as the per-head kernel it replaces
+    old = kernels.cross_attention(q.cuda(), k.contiguous(), v.contiguous(), bits.cuda(), row_open.cuda(), nh)
+    _close(out, old.float().cpu(), dt)
+
+
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
 def test_mask_head_kernels(dt):
     torch.manual_seed(0)

@@ -45,6 +45,10 @@ def test_parity_metrics_on_emulated_pipeline(monkeypatch):
     forced = parity.forced_stage_errors(m, it, inp["images"])
     assert max(free.values()) < 1e-3, free
     assert max(forced.values()) < 1e-3, forced
+    layers = parity.forced_layer_errors(m, it)
+    assert layers["layer_l2rel_max"] < 1e-4 and layers["mask_bit_agree_min"] > 0.9999, layers
+    sens = parity.predictor_sensitivity(sd, it, torch.bfloat16)
+    assert sens["pred_masks_l2rel"] > 1e-4      # bf16 input rounding alone moves the reference's own output
     # a corrupted result must show up
     bad = dict(out, pred_masks=out["pred_masks"] * 1.05)
     assert parity.final_metrics(bad, it)["mask_logit_maxrel"] > 1e-2
