@@ -75,10 +75,16 @@ int psalm_msda_forward(const void* value, const int64_t* shapes, const int64_t* 
  *          dtype ow_dtype (F32 / F16 / BF16).  Lq must equal S (encoder self-attention).
  *   out    [B,Lq,M*D] dtype value_dtype
  *   shapes_host/starts_host: HOST int64 arrays.
- * Two lane mappings: one lane group per (query, head) (default, measured faster) and paired columns (2*D/8 lanes
- * per (query, head), the two x-adjacent bilinear corners are one contiguous access).  psalm_set_msda_impl:
- * 0 = auto, 1 = single group, 2 = paired columns. */
+ * Three kernels sit behind the call (psalm_set_msda_impl: 0 = auto (= 1), 1, 2, 3):
+ *   1  one lane group per (query, head), corners gathered from global memory / L1 (measured fastest);
+ *   2  paired columns (the two x-adjacent bilinear corners are one contiguous access);
+ *   3  (16-bit storage, M=8, D=32, L=3, P=4, levels ordered coarse to fine) value tiles of a 16x16 cell of the finest
+ *      level (+ halo) staged in shared memory by TMA (cp.async.bulk.tensor.4d, zero fill = the op's zero padding), the
+ *      gather + weighted sum as ldmatrix gathers + mma.sync (csrc/msda_smem.cu); samples beyond the halo
+ *      (psalm_set_msda_halo, default 5 pixels) read global memory - results do not depend on the halo.  Correct,
+ *      selectable, measured slower than 1. */
 int psalm_set_msda_impl(int impl);
+int psalm_set_msda_halo(int halo);
 int psalm_msda_encoder_fused(const void* value, const void* ow, void* out,
                              const int64_t* shapes_host, const int64_t* starts_host,
                              int B, int S, int M, int D, int L, int P,
@@ -212,6 +218,22 @@ size_t psalm_masked_cross_attention_workspace_bytes(int B, int Lq, int Lk);
 int psalm_masked_cross_attention(const void* q, const void* k, const void* v, long long kv_row_stride,
                                  const uint32_t* mask_bits, const uint8_t* row_open, void* out, float* workspace,
                                  size_t workspace_bytes, int B, int Lq, int Lk, int nh, int hd, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Autoregressive decode of the LLM (chat path: psalm/serve/cli.py:89-96 -> PSALM.generate; single-token branch
+ * language_model/llava_phi.py:773-778): paged KV cache + single-token causal attention (csrc/decode.cu).
+ * Replaces HF's DynamicCache growth by torch.cat (a full cache copy per layer per token) and the eager
+ * [B,32,1,T] score / softmax / matmul chain of PhiAttention.
+ *   cache pages  [num_pages, nh, page_size, hd] (K and V separately), block_table [B,max_pages] int32
+ *   psalm_kv_cache_write: rows t = 0..T-1 of qkv [B,T,3,nh,hd] (rotary applied) go to positions start_pos[b] + t
+ *   psalm_paged_decode_attention: q [B,nh,hd] with batch stride q_batch_stride elements (e.g. 3*nh*hd inside a qkv
+ *     buffer) against the first seq_lens[b] cached keys -> out [B, nh*hd]
+ * ------------------------------------------------------------------------------------------ */
+int psalm_kv_cache_write(const void* qkv, void* kcache, void* vcache, const int* block_table, const int* start_pos, int B,
+                         int T, int nh, int hd, int page_size, int max_pages, int dtype, void* stream);
+int psalm_paged_decode_attention(const void* q, long long q_batch_stride, const void* kcache, const void* vcache,
+                                 const int* block_table, const int* seq_lens, void* out, int B, int nh, int hd, int page_size,
+                                 int max_pages, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Input pipeline on the device: pixel normalisation + zero padding to the patch grid +

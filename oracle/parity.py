@@ -175,11 +175,11 @@ class _LayerTeacher:
         nbits = blocked.numel()
         nflip = sum(int(((flips >> k) & 1).sum()) for k in range(32))
         self.mask_agree.append(1.0 - nflip / nbits)
-        # flips away from the decision threshold (|oracle mask logit| at the target size > 1e-2 of its rms)
+        # flips away from the decision threshold (|oracle mask logit| at the target size > 5e-2 of its rms)
         lg = torch.nn.functional.interpolate(self.po["trace"][i][2].float(), size=self.sizes[i % 3], mode="bilinear",
                                              align_corners=False).flatten(2)
         hw = blocked.shape[-1]
-        firm = lg.abs() > 1e-2 * lg.pow(2).mean().sqrt()
+        firm = lg.abs() > 5e-2 * lg.pow(2).mean().sqrt()
         bit = torch.stack([((flips >> k) & 1) for k in range(32)], -1).view(B, blocked.shape[1], -1)[..., :hw].bool()
         self.mask_agree_off_threshold.append(1.0 - float((bit & firm).sum()) / max(1, int(firm.sum())))
         return state, rb.to(self.m.device), ro.to(self.m.device)

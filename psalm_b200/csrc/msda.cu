@@ -248,7 +248,7 @@ __global__ void msda_scalar_kernel(const TV* __restrict__ value, const TL* __res
 // addresses), 16 bytes per lane.
 // -------------------------------------------------------------------------------------------
 template <typename TV, typename TO, int G, int LT, int PT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)   // <= 64 registers: 4 CTAs per SM (65 registers gave 3: occupancy 37.5 % -> 50 %)
 msda_encoder_fused_kernel(const TV* __restrict__ value, const TO* __restrict__ ow,
                           TV* __restrict__ out, MsdaLevels lv, int S, int M, int D) {
   constexpr int CH = 16 / sizeof(TV);
@@ -599,7 +599,12 @@ msda_encoder_fused_pair_kernel(const TV* __restrict__ value, const TO* __restric
   if (active && half == 0) store16_from_f32<TV>(out + (((size_t)b * S + q) * M + m) * (size_t)DC + cl * CH, acc);
 }
 
-int g_msda_fused_impl = 0;   // 0 auto (= 1: measured faster), 1 one lane group per (query, head), 2 paired columns
+int g_msda_fused_impl = 0;   // 0 auto, 1 one lane group per (query, head), 2 paired columns, 3 TMA-staged tiles + mma (msda_smem.cu)
+
+// TMA-staged shared-memory tiles + tensor-core contraction (msda_smem.cu): 16-bit storage, M = 8, D = 32, L = 3, P = 4
+bool msda_smem_ok(int M, int D, int L, int P, int value_dtype, const int64_t* shapes_host);
+int msda_smem_fused(const void* value, const void* ow, void* out, const int64_t* shapes_host, const int64_t* starts_host, int B,
+                    int S, int value_dtype, int ow_dtype, cudaStream_t st);
 
 template <typename TV, typename TO>
 static int launch_fused(const void* value, const void* ow, void* out, const int64_t* shapes_host,
@@ -662,7 +667,7 @@ extern "C" int psalm_msda_forward(const void* value, const int64_t* shapes, cons
 }
 
 extern "C" int psalm_set_msda_impl(int impl) {
-  PSALM_REQUIRE(impl >= 0 && impl <= 2, "set_msda_impl: 0 (auto), 1 (one lane group per query-head) or 2 (paired columns)");
+  PSALM_REQUIRE(impl >= 0 && impl <= 3, "set_msda_impl: 0 (auto), 1 (one lane group per query-head), 2 (paired columns) or 3 (TMA tiles)");
   psalm::g_msda_fused_impl = impl;
   return PSALM_OK;
 }
@@ -674,6 +679,18 @@ extern "C" int psalm_msda_encoder_fused(const void* value, const void* ow, void*
   PSALM_REQUIRE(value && ow && out && shapes_host && starts_host, "msda_fused: null pointer argument");
   PSALM_REQUIRE(B > 0 && S > 0 && M > 0 && D > 0, "msda_fused: non-positive dimension");
   cudaStream_t st = (cudaStream_t)stream;
+  // auto = the L1-gather kernel: the TMA-tile + mma kernel (impl 3) is correct but measured slower at 1024^2
+  // (84 us vs 53 us per layer-image: 53.7 M vs 39 M warp instructions)
+  if (g_msda_fused_impl == 3) {
+    const bool ok = msda_smem_ok(M, D, L, P, value_dtype, shapes_host) && M <= 65535 && B <= 65535;
+    if (ok) {
+      long long sum = 0;
+      for (int l = 0; l < L; ++l) sum += shapes_host[2 * l] * shapes_host[2 * l + 1];
+      PSALM_REQUIRE(sum == S, "msda_fused: sum(H_l*W_l)=%lld != S=%d", sum, S);
+      return msda_smem_fused(value, ow, out, shapes_host, starts_host, B, S, value_dtype, ow_dtype, st);
+    }
+    PSALM_REQUIRE(false, "msda_fused: the TMA-tile kernel needs 16-bit storage, M=8, D=32, L=3, P=4, levels coarse to fine");
+  }
 #define ARGS value, ow, out, shapes_host, starts_host, B, S, M, D, L, P, st
   if (value_dtype == PSALM_F32 && ow_dtype == PSALM_F32) return launch_fused<float, float>(ARGS);
   if (value_dtype == PSALM_F16 && ow_dtype == PSALM_F16) return launch_fused<__half, __half>(ARGS);

@@ -347,3 +347,34 @@ def masked_cross_attention(q, k, v, mask_bits=None, row_open=None, nh=8, workspa
     _lib.check(rc, "psalm_masked_cross_attention")
     _count(2 if need else 1)
     return out
+
+
+@_on_device
+def kv_cache_write(qkv, kcache, vcache, block_table, start_pos):
+    """qkv [B,T,3,nh,hd] (rotary applied): K / V rows of the T tokens -> cache pages [num_pages,nh,page,hd] at positions
+    start_pos[b] + t through block_table [B,max_pages] (int32)."""
+    _chk(qkv, "kv_cache_write.qkv")
+    B, T, _, nh, hd = qkv.shape
+    rc = _lib.lib().psalm_kv_cache_write(_lib.ptr(qkv), _lib.ptr(kcache), _lib.ptr(vcache), _lib.ptr(block_table),
+                                         _lib.ptr(start_pos), B, T, nh, hd, kcache.shape[2], block_table.shape[1],
+                                         _lib.dtype_code(qkv.dtype), _lib.stream_ptr(qkv.device))
+    _lib.check(rc, "psalm_kv_cache_write")
+    _count()
+
+
+@_on_device
+def paged_decode_attention(qkv, kcache, vcache, block_table, seq_lens):
+    """qkv [B,1,3,nh,hd] of the new token (its K / V already written to the cache) -> [B,1,nh*hd]: attention of the new
+    query over the first seq_lens[b] cached keys."""
+    _chk(qkv, "paged_decode_attention.qkv")
+    B, T, _, nh, hd = qkv.shape
+    if T != 1:
+        raise _lib.PsalmKernelError("paged_decode_attention: one query token per sequence")
+    out = torch.empty((B, 1, nh * hd), dtype=qkv.dtype, device=qkv.device)
+    rc = _lib.lib().psalm_paged_decode_attention(_lib.ptr(qkv), 3 * nh * hd, _lib.ptr(kcache), _lib.ptr(vcache),
+                                                 _lib.ptr(block_table), _lib.ptr(seq_lens), _lib.ptr(out), B, nh, hd,
+                                                 kcache.shape[2], block_table.shape[1], _lib.dtype_code(qkv.dtype),
+                                                 _lib.stream_ptr(qkv.device))
+    _lib.check(rc, "psalm_paged_decode_attention")
+    _count()
+    return out

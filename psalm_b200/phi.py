@@ -45,8 +45,9 @@ class PhiModel:
     def __call__(self, inputs_embeds, attention_mask=None):
         return self.forward(inputs_embeds, attention_mask)
 
-    def forward(self, inputs_embeds, attention_mask=None):
-        """inputs_embeds [B,T,C]; attention_mask [B,T] (True/1 = real token) or None -> last_hidden_state."""
+    def forward(self, inputs_embeds, attention_mask=None, cache=None):
+        """inputs_embeds [B,T,C]; attention_mask [B,T] (True/1 = real token) or None -> last_hidden_state.
+        `cache` (generate.PagedKVCache): the rotary-applied K / V rows of every layer are also written to its pages."""
         cfg, w = self.cfg, self.w
         B, T, C = inputs_embeds.shape
         nh, hd = cfg.heads, cfg.head_dim
@@ -64,10 +65,38 @@ class PhiModel:
                 h, x = kernels.add_layer_norm(h, w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps, r1=a, r2=f, return_sum=True)
             qkv = F.linear(x, w["%d.qkv.w" % i], w["%d.qkv.b" % i]).view(B, T, 3, nh, hd)
             kernels.rotary_inplace(qkv, cos, sin, B, T, nh, hd, rd)
+            if cache is not None:
+                kernels.kv_cache_write(qkv, cache.k[i], cache.v[i], cache.block_table, cache.seq_lens)
             a = kernels.timed("causal_attention", kernels.causal_attention, qkv, kv, B, T, nh, hd)
             a = F.linear(a, w["%d.dense.w" % i], w["%d.dense.b" % i])
             f = self._fc1_gelu(x, i)
             f = F.linear(f, w["%d.fc2.w" % i], w["%d.fc2.b" % i])
+        return kernels.add_layer_norm(h, w["fln.w"], w["fln.b"], cfg.eps, r1=a, r2=f)
+
+    def decode_step(self, x, cache):
+        """One autoregressive step: x [B,1,C] = embedding of the newest token of every sequence, position cache.length
+        (all sequences have the same length).  Appends its K / V to the cache and returns the final hidden state [B,1,C].
+        (PhiDecoderLayer with past_key_values, single-token branch of llava_phi.py:773-778.)"""
+        cfg, w = self.cfg, self.w
+        B, T, C = x.shape
+        nh, hd = cfg.heads, cfg.head_dim
+        rd = int(hd * cfg.rotary_frac)
+        pos = cache.length
+        cos, sin = self.rope_tables(cache.max_len)
+        cos, sin = cos[pos:pos + 1].contiguous(), sin[pos:pos + 1].contiguous()
+        h = x.contiguous()
+        a = f = None
+        for i in range(cfg.layers):
+            if a is None:
+                y = kernels.add_layer_norm(h, w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps)
+            else:
+                h, y = kernels.add_layer_norm(h, w["%d.ln.w" % i], w["%d.ln.b" % i], cfg.eps, r1=a, r2=f, return_sum=True)
+            qkv = F.linear(y, w["%d.qkv.w" % i], w["%d.qkv.b" % i]).view(B, 1, 3, nh, hd)
+            kernels.rotary_inplace(qkv, cos, sin, B, 1, nh, hd, rd)
+            kernels.kv_cache_write(qkv, cache.k[i], cache.v[i], cache.block_table, cache.seq_lens)
+            a = kernels.paged_decode_attention(qkv, cache.k[i], cache.v[i], cache.block_table, cache.seq_lens_plus1)
+            a = F.linear(a, w["%d.dense.w" % i], w["%d.dense.b" % i])
+            f = F.linear(self._fc1_gelu(y, i), w["%d.fc2.w" % i], w["%d.fc2.b" % i])
         return kernels.add_layer_norm(h, w["fln.w"], w["fln.b"], cfg.eps, r1=a, r2=f)
 
     def _fc1_gelu(self, x, i):

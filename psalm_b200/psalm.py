@@ -78,6 +78,10 @@ class PSALM:
         self.seg_query = cv(sd["seg_query"])
         self.proj = {n: (cv(sd[n + ".weight"]), cv(sd[n + ".bias"]))
                      for n in ("seg_query_projector", "SEG_token_projector", "class_name_projector")}
+        # lm_head (no bias in the reference, llava_phi.py:191): only the chat / decode path reads it
+        self.lm_head = None
+        if "lm_head.weight" in sd:
+            self.lm_head = (cv(sd["lm_head.weight"]), cv(sd["lm_head.bias"]) if "lm_head.bias" in sd else None)
         self.num_queries = cfg.mask.num_queries
         self.test_topk_per_image = cfg.mask.num_queries
         self.size_divisibility = cfg.mask.size_divisibility
@@ -123,6 +127,51 @@ class PSALM:
     @classmethod
     def from_state_dict(cls, sd, **kw):
         return cls(sd, **kw)
+
+    @classmethod
+    def from_pretrained(cls, model_path, mask_decoder_cfg=None, **kw):
+        """Checkpoint directory of the reference (config.json + safetensors / bin shards), keys unchanged
+        (psalm/model/builder.py:55 calls this on the reference class)."""
+        from .builder import from_pretrained
+        return from_pretrained(cls, model_path, mask_decoder_cfg, **kw)
+
+    def generate(self, input_ids=None, images=None, max_new_tokens=32, do_sample=False, temperature=1.0, top_p=None,
+                 eos_token_id=None, **_unused):
+        """Chat / decoding path (psalm/serve/cli.py:89-96): prefill + autoregressive decode with a paged KV cache
+        (psalm_b200/generate.py).  Returns the NEW token ids [B, n_new]."""
+        from .generate import generate
+        return generate(self, input_ids, images, max_new_tokens, do_sample, temperature, top_p, eos_token_id)
+
+    # ---- LlavaMetaForCausalLM methods the training / serving scripts call by name -------------------
+    def initialize_vision_tokenizer(self, model_args, tokenizer):
+        """llava_arch.py:181-217.  The released checkpoints set mm_use_im_patch_token = mm_use_im_start_end = False, for
+        which the reference method does nothing; growing the embedding table is a training-time operation."""
+        if getattr(model_args, "mm_use_im_patch_token", False) or getattr(model_args, "mm_use_im_start_end", False):
+            raise NotImplementedError("adding image patch / start / end tokens resizes the embedding table: training-time "
+                                      "surface, outside this inference build")
+
+    def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images,
+                                             class_name_embedding_indices=None, class_name_ids=None, cls_indices=None,
+                                             instances=None, token_refer_id=None, refer_embedding_indices=None):
+        """llava_phi.py:767-971: sentinel ids -> embeddings.  Returns the reference's tuple
+        (input_ids=None, attention_mask, past_key_values, inputs_embeds, labels, seg_query_mask,
+         class_name_embedding_indices, region_embedding_masks, refer_embedding_indices) for the image-prefill case."""
+        if instances is not None:
+            raise NotImplementedError("<region> prompts are outside this build's scope (SURVEY.md section 8 f3)")
+        with self._precision_scope():
+            img_tok = self.encode_images(images.to(self.device))
+        plan = self.make_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
+                              class_name_embedding_indices, token_refer_id, refer_embedding_indices).to(self.device)
+        embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query)
+        B, T = plan.B, plan.T
+        flat = lambda pos: torch.zeros(B * T, device=self.device).index_fill_(0, pos, 1.0).view(B, T)   # noqa: E731
+        seg_query_mask = flat(plan.seg_pos)
+        cls_idx = None
+        if plan.cls_pool is not None:     # class index (1-based) of every position, 0 elsewhere (:671-673)
+            cls_idx = ((plan.cls_pool > 0).float() * torch.arange(1, plan.cls_pool.shape[1] + 1, device=self.device)
+                       .view(1, -1, 1)).sum(1).long()
+        ref_idx = (plan.refer_pool[:, 0] > 0).long() if plan.refer_pool is not None else None
+        return None, plan.attention_mask, past_key_values, embeds, labels, seg_query_mask, cls_idx, None, ref_idx
 
     # ---- LlavaMetaForCausalLM surface --------------------------------------------------------------
     def get_model(self):

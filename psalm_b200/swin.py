@@ -34,7 +34,8 @@ def _rel_index(ws):
 class SwinTransformer:
     def __init__(self, sd, prefix="model.vision_tower.", cfg=SwinConfig(), dtype=torch.bfloat16, device="cuda"):
         self.cfg, self.dtype, self.device = cfg, dtype, device
-        self.image_processor = {}
+        from .image_processor import build_image_processors
+        self.image_processor = build_image_processors()   # panoptic | instance | semantic (llava_phi.py:66-69)
         # pixel statistics of the reference's dataset mappers (datasets_mapper/coco_panoptic_mapper.py:118-119):
         # uint8 images are normalised on the device with them
         self.pixel_mean = torch.tensor([123.675, 116.28, 103.53], dtype=torch.float32, device=device)

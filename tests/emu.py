@@ -147,10 +147,36 @@ def patchify(images, out_dtype, mean=None, std=None, patch=4):
     return x.to(out_dtype), (Wh, Ww)
 
 
+def kv_cache_write(qkv, kcache, vcache, block_table, start_pos):
+    B, T, _, nh, hd = qkv.shape
+    ps = kcache.shape[2]
+    for b in range(B):
+        for t in range(T):
+            pos = int(start_pos[b]) + t
+            page, slot = int(block_table[b, pos // ps]), pos % ps
+            kcache[page, :, slot] = qkv[b, t, 1]
+            vcache[page, :, slot] = qkv[b, t, 2]
+
+
+def paged_decode_attention(qkv, kcache, vcache, block_table, seq_lens):
+    B, _, _, nh, hd = qkv.shape
+    ps = kcache.shape[2]
+    out = torch.empty(B, 1, nh * hd, dtype=qkv.dtype)
+    for b in range(B):
+        n = int(seq_lens[b])
+        pages = block_table[b, : (n + ps - 1) // ps].long()
+        k = kcache[pages].permute(1, 0, 2, 3).reshape(nh, -1, hd)[:, :n].float()
+        v = vcache[pages].permute(1, 0, 2, 3).reshape(nh, -1, hd)[:, :n].float()
+        s = torch.einsum("hd,hkd->hk", qkv[b, 0, 0].float(), k) * hd ** -0.5
+        out[b, 0] = torch.einsum("hk,hkd->hd", s.softmax(-1), v).reshape(-1).to(qkv.dtype)
+    return out
+
+
 def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
-                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify", "masked_cross_attention"):
+                 "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify", "masked_cross_attention", "kv_cache_write",
+                 "paged_decode_attention"):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 

@@ -97,16 +97,19 @@ def _fused_inputs(shapes, B, M, D, L, P, seed):
 
 
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
-@pytest.mark.parametrize("impl", [1, 2], ids=["single-group", "paired-columns"])
-@pytest.mark.parametrize("shapes", [[(6, 9), (12, 18), (24, 36)], [(5, 7), (11, 13), (21, 27)]], ids=["even", "odd"])
+@pytest.mark.parametrize("impl", [1, 2, 3], ids=["single-group", "paired-columns", "tma-tiles"])
+@pytest.mark.parametrize("shapes", [[(6, 9), (12, 18), (24, 36)], [(5, 7), (11, 13), (21, 27)], [(16, 16), (32, 32), (64, 64)],
+                                    [(42, 42), (84, 84), (167, 167)]], ids=["even", "odd", "pow2", "ade1333"])
 def test_fused_encoder_kernel(dt, impl, shapes):
     """softmax + reference points + location arithmetic fused in-kernel equals the unfused module
     arithmetic (ops/modules/ms_deform_attn.py:103-110 + get_reference_points, msdeformattn.py:76-87);
     both lane mappings of the kernel, even and odd map widths (ragged tiles, unaligned column pairs)."""
     from oracle import psalm_oracle as O
     from psalm_b200 import _lib
+    if impl == 3 and dt == "f32":
+        pytest.skip("the TMA-tile kernel is the 16-bit storage path")
     B, M, D, L, P = 2, 8, 32, 3, 4
-    value, off, logit = _fused_inputs(shapes, B, M, D, L, P, 1)
+    value, off, logit = _fused_inputs(shapes, B, M, D, L, P, 1)    # offsets ~ N(0, 3^2): ~10 % of the samples leave a 5-pixel halo
     S = value.shape[1]
     tdt = DT[dt]
     vq = torch.from_numpy(value).to(tdt)
@@ -125,7 +128,12 @@ def test_fused_encoder_kernel(dt, impl, shapes):
     loc = ref_pts[:, :, None, :, None, :] + offq.double() / normalizer[None, None, None, :, None, :]
     aw = torch.softmax(lgq.double(), -1).view(B, S, M, L, P)
     ref = msda_oracle.msda_ref(vq.double().numpy(), np.array(shapes), loc.numpy(), aw.numpy(), np.float64)
-    _check(out.double().cpu().numpy(), ref, dt)
+    if dt == "f32" and max(w for _, w in shapes) > 100:
+        # fp32 sampling positions (ref * W + offset) carry an absolute error ~ ulp(W): 1.4e-5 of the output at W = 167
+        scale = np.abs(ref).max()
+        assert np.abs(out.double().cpu().numpy() - ref).max() / scale < 4e-5
+    else:
+        _check(out.double().cpu().numpy(), ref, dt)
 
 
 def test_full_size_properties():
