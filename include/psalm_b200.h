@@ -199,6 +199,19 @@ int psalm_postproc_fused(const void* logits, const void* probsT_f16, const float
                          unsigned char* in_mask, float* partials, int Q, int H4, int W4, int H, int W, int ncls,
                          int K, int dtype, void* stream);
 
+/* Same outputs for the reference's eval flow with a padded / resized image (detectron2 sem_seg_postprocess inside
+ * eval_seg, llava_phi.py:1418-1430): the low-resolution logits are up-sampled to the padded input size (Hp, Wp), cropped
+ * to the un-padded box (oh, ow) and resized to the output size (H, W) - composed inside the kernel (4 x 4 separable taps
+ * per pixel), the [Q,Hp,Wp] tensor never exists.  psalm_postproc_crop_supported: 1 when the geometry fits the kernel's
+ * shared-memory source window (otherwise callers use the step-by-step path).  partials rows:
+ * psalm_postproc_crop_partials(H, W). */
+int psalm_postproc_crop_supported(int Q, int H4, int W4, int Hp, int Wp, int oh, int ow, int H, int W, int ncls);
+int psalm_postproc_crop_partials(int H, int W, int* rows);
+int psalm_postproc_fused_crop(const void* logits, const void* probsT_f16, const float* wq, const float* negq,
+                              const int* slot_query, float* sem_seg, float* inst_masks, int* ids, unsigned char* in_mask,
+                              float* partials, int Q, int H4, int W4, int Hp, int Wp, int oh, int ow, int H, int W,
+                              int ncls, int K, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Masked cross-attention of the Mask2Former decoder, all 8 heads of a key range per CTA, K/V through TMA
  * (csrc/xattn_tma.cu).  Same mathematics as psalm_cross_attention; replaces CrossAttentionLayer.forward_post's

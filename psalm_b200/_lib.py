@@ -49,6 +49,9 @@ SIGNATURES = {
     "psalm_set_causal_impl": ([_c_i], _c_i),
     "psalm_postproc_partials": ([_c_i] * 8 + [ctypes.POINTER(_c_i)], _c_i),
     "psalm_postproc_fused": ([_c_vp] * 10 + [_c_i] * 8 + [_c_vp], _c_i),
+    "psalm_postproc_crop_supported": ([_c_i] * 10, _c_i),
+    "psalm_postproc_crop_partials": ([_c_i] * 2 + [ctypes.POINTER(_c_i)], _c_i),
+    "psalm_postproc_fused_crop": ([_c_vp] * 10 + [_c_i] * 12 + [_c_vp], _c_i),
     "psalm_add_layernorm": ([_c_vp] * 7 + [ctypes.c_longlong, _c_i, ctypes.c_float, _c_i, _c_vp], _c_i),
     "psalm_set_cross_impl": ([_c_i], _c_i),
     "psalm_masked_cross_attention_workspace_bytes": ([_c_i] * 3, ctypes.c_size_t),

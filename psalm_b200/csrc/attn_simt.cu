@@ -320,6 +320,39 @@ __global__ void rotary_kernel(T* __restrict__ qkv, const float* __restrict__ cs,
   }
 }
 
+// 16-byte vector form for 16-bit storage and rd / 2 a multiple of 8: one thread rotates 8 (x1, x2) pairs
+// (the scalar kernel moved 2 bytes per load: 28 us per layer at 4 x 920 tokens against ~5 us of HBM time)
+template <typename T>
+__global__ void __launch_bounds__(256) rotary_vec_kernel(T* __restrict__ qkv, const float* __restrict__ cs,
+                                                         const float* __restrict__ sn, int B, int T_, int nh, int hd, int rd) {
+  const int half = rd / 2, chunks = half / 8;
+  const long long n = (long long)B * T_ * 2 * nh * chunks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int c = (int)(t % chunks); t /= chunks;
+    const int h = (int)(t % nh); t /= nh;
+    const int which = (int)(t % 2); t /= 2;
+    const int pos = (int)(t % T_);
+    const int b = (int)(t / T_);
+    T* p = qkv + ((((size_t)b * T_ + pos) * 3 + which) * nh + h) * hd + c * 8;
+    float x1[8], x2[8], co[8], si[8], y1[8], y2[8];
+    load16_as_f32<T>(p, x1);
+    load16_as_f32<T>(p + half, x2);
+    const float4* c4 = reinterpret_cast<const float4*>(cs + (size_t)pos * half + c * 8);
+    const float4* s4 = reinterpret_cast<const float4*>(sn + (size_t)pos * half + c * 8);
+    const float4 ca = __ldg(c4), cb = __ldg(c4 + 1), sa = __ldg(s4), sb = __ldg(s4 + 1);
+    co[0] = ca.x; co[1] = ca.y; co[2] = ca.z; co[3] = ca.w; co[4] = cb.x; co[5] = cb.y; co[6] = cb.z; co[7] = cb.w;
+    si[0] = sa.x; si[1] = sa.y; si[2] = sa.z; si[3] = sa.w; si[4] = sb.x; si[5] = sb.y; si[6] = sb.z; si[7] = sb.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      y1[i] = x1[i] * co[i] - x2[i] * si[i];
+      y2[i] = x2[i] * co[i] + x1[i] * si[i];
+    }
+    store16_from_f32<T>(p, y1);
+    store16_from_f32<T>(p + half, y2);
+  }
+}
+
 }  // namespace psalm
 
 namespace psalm {
@@ -401,6 +434,13 @@ extern "C" int psalm_rotary_inplace(void* qkv, const float* cos_t, const float* 
                                     int hd, int rd, int dtype, void* stream) {
   PSALM_REQUIRE(qkv && cos_t && sin_t, "rotary: null pointer");
   PSALM_REQUIRE(rd % 2 == 0 && rd <= hd, "rotary: bad rotary dim %d (head dim %d)", rd, hd);
+  if (dtype != PSALM_F32 && (rd / 2) % 8 == 0 && hd % 8 == 0) {
+    const long long nv = (long long)B * T_ * 2 * nh * (rd / 16);
+    const int vb = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+    if (dtype == PSALM_BF16) rotary_vec_kernel<__nv_bfloat16><<<vb > 0 ? vb : 1, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv, cos_t, sin_t, B, T_, nh, hd, rd);
+    else rotary_vec_kernel<__half><<<vb > 0 ? vb : 1, 256, 0, (cudaStream_t)stream>>>((__half*)qkv, cos_t, sin_t, B, T_, nh, hd, rd);
+    return check_launch("rotary_vec_kernel");
+  }
   const long long n = (long long)B * T_ * 2 * nh * (rd / 2);
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   DISPATCH_T(dtype, {

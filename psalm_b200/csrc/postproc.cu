@@ -52,9 +52,12 @@ struct PostprocArgs {
   unsigned char* in_mask;  // [H, W]
   float* partials;         // [n_cta, Q, 5]: pos_cnt, pos_sig, ge_cnt, area, inter
   int Q, H4, W4, H, W, ncls, K;
+  // composed resampling (sem_seg_postprocess, llava_phi.py:1399-1430): up-sample to the padded input size (Hp, Wp), crop
+  // to the un-padded box (oh, ow), resize to the output size (H, W).  composed == 0: (H, W) is the up-sampled size itself.
+  int composed, Hp, Wp, oh, ow;
 };
 
-template <typename T>
+template <typename T, bool COMPOSED>
 __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* src = reinterpret_cast<float*>(smem_raw);                               // [PP_SRC_MAX][PP_SLD]
@@ -70,12 +73,23 @@ __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Q = a.Q;
   const int ty0 = blockIdx.y * PP_TH, tx0 = blockIdx.x * PP_TW;
-  const float sh = (float)a.H4 / (float)a.H, sw = (float)a.W4 / (float)a.W;
+  // low-resolution scale: to the output size, or (composed) to the padded input size; second stage: crop -> output
+  const float sh = COMPOSED ? (float)a.H4 / (float)a.Hp : (float)a.H4 / (float)a.H;
+  const float sw = COMPOSED ? (float)a.W4 / (float)a.Wp : (float)a.W4 / (float)a.W;
+  const float sh2 = COMPOSED ? (float)a.oh / (float)a.H : 1.f, sw2 = COMPOSED ? (float)a.ow / (float)a.W : 1.f;
   // source window of this tile (ATen area_pixel_compute_source_index, align_corners = false)
   auto srcf = [](float scale, int d) { const float s = scale * ((float)d + 0.5f) - 0.5f; return s < 0.f ? 0.f : s; };
   const int ylast = min(ty0 + PP_TH, a.H) - 1, xlast = min(tx0 + PP_TW, a.W) - 1;
-  const int sy0 = (int)srcf(sh, ty0), sx0 = (int)srcf(sw, tx0);
-  const int sy1 = min((int)srcf(sh, ylast) + 1, a.H4 - 1), sx1 = min((int)srcf(sw, xlast) + 1, a.W4 - 1);
+  int sy0, sx0, sy1, sx1;
+  if (COMPOSED) {   // output rows -> rows of the cropped up-sampled image -> low-resolution rows
+    const int Y0 = (int)srcf(sh2, ty0), Y1 = min((int)srcf(sh2, ylast) + 1, a.oh - 1);
+    const int X0 = (int)srcf(sw2, tx0), X1 = min((int)srcf(sw2, xlast) + 1, a.ow - 1);
+    sy0 = (int)srcf(sh, Y0); sx0 = (int)srcf(sw, X0);
+    sy1 = min((int)srcf(sh, Y1) + 1, a.H4 - 1); sx1 = min((int)srcf(sw, X1) + 1, a.W4 - 1);
+  } else {
+    sy0 = (int)srcf(sh, ty0); sx0 = (int)srcf(sw, tx0);
+    sy1 = min((int)srcf(sh, ylast) + 1, a.H4 - 1); sx1 = min((int)srcf(sw, xlast) + 1, a.W4 - 1);
+  }
   const int SR = sy1 - sy0 + 1, SC = sx1 - sx0 + 1;
 
   for (int i = tid; i < PP_QP * 5; i += 256) stats[i] = 0.f;
@@ -97,19 +111,58 @@ __global__ void __launch_bounds__(256) postproc_fused_kernel(PostprocArgs a) {
   const int p = tid & (PP_PIX - 1), half = tid >> 7;
   const int py = ty0 + p / PP_TW, px = tx0 + p % PP_TW;
   const bool inb = py < a.H && px < a.W;
-  const float fy = srcf(sh, py < a.H ? py : a.H - 1), fx = srcf(sw, px < a.W ? px : a.W - 1);
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = y0 + (y0 < a.H4 - 1 ? 1 : 0), x1 = x0 + (x0 < a.W4 - 1 ? 1 : 0);
-  const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-  const int o00 = ((y0 - sy0) * SC + (x0 - sx0)) * PP_SLD, o01 = ((y0 - sy0) * SC + (x1 - sx0)) * PP_SLD;
-  const int o10 = ((y1 - sy0) * SC + (x0 - sx0)) * PP_SLD, o11 = ((y1 - sy0) * SC + (x1 - sx0)) * PP_SLD;
+  const int pyc = py < a.H ? py : a.H - 1, pxc = px < a.W ? px : a.W - 1;
+  // separable taps: NT rows x NT columns of the source window with weights wy[i] * wx[j]; one stage: 2 x 2, composed: the
+  // two rows (columns) of the cropped up-sampled image each expand to two low-resolution rows (columns): 4 x 4
+  constexpr int NT = COMPOSED ? 4 : 2;
+  int oy[NT], ox[NT];
+  float wy[NT], wx[NT];
+  {
+    auto taps = [&](float scale, int n_lo, int lo0, float coord, int& i0, int& i1, float& w0, float& w1) {
+      const int c0 = (int)coord;
+      const int c1 = c0 + (c0 < n_lo - 1 ? 1 : 0);
+      const float l = coord - (float)c0;
+      i0 = c0 - lo0; i1 = c1 - lo0; w0 = 1.f - l; w1 = l;
+    };
+    if (COMPOSED) {
+      const float fY = srcf(sh2, pyc), fX = srcf(sw2, pxc);
+      const int Y0 = (int)fY, X0 = (int)fX;
+      const int Y1 = Y0 + (Y0 < a.oh - 1 ? 1 : 0), X1 = X0 + (X0 < a.ow - 1 ? 1 : 0);
+      const float lY = fY - (float)Y0, lX = fX - (float)X0;
+      float w0, w1;
+      taps(sh, a.H4, sy0, srcf(sh, Y0), oy[0], oy[1], w0, w1); wy[0] = (1.f - lY) * w0; wy[1] = (1.f - lY) * w1;
+      taps(sh, a.H4, sy0, srcf(sh, Y1), oy[2], oy[3], w0, w1); wy[2] = lY * w0; wy[3] = lY * w1;
+      taps(sw, a.W4, sx0, srcf(sw, X0), ox[0], ox[1], w0, w1); wx[0] = (1.f - lX) * w0; wx[1] = (1.f - lX) * w1;
+      taps(sw, a.W4, sx0, srcf(sw, X1), ox[2], ox[3], w0, w1); wx[2] = lX * w0; wx[3] = lX * w1;
+    } else {
+      taps(sh, a.H4, sy0, srcf(sh, pyc), oy[0], oy[1], wy[0], wy[1]);
+      taps(sw, a.W4, sx0, srcf(sw, pxc), ox[0], ox[1], wx[0], wx[1]);
+    }
+  }
+  int off[NT][NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) off[i][j] = (oy[i] * SC + ox[j]) * PP_SLD;
   float best_v = -2.f, best_x = 0.f;
   int best_q = 0;
   const int wsub = warp & 3;   // which 32-pixel group of the tile this warp covers
   const float* wqp = a.wq;
   const float* ngp = a.negq;
   for (int q = half; q < Q; q += 2) {
-    const float x = hy * (hx * src[o00 + q] + lx * src[o01 + q]) + ly * (hx * src[o10 + q] + lx * src[o11 + q]);
+    float x;
+    if (COMPOSED) {
+      x = 0.f;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        float r = 0.f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) r = fmaf(wx[j], src[off[i][j] + q], r);
+        x = fmaf(wy[i], r, x);
+      }
+    } else {
+      x = wy[0] * (wx[0] * src[off[0][0] + q] + wx[1] * src[off[0][1] + q]) + wy[1] * (wx[0] * src[off[1][0] + q] + wx[1] * src[off[1][1] + q]);
+    }
     const float s = __fdividef(1.f, 1.f + __expf(-x));
     Bs[q * PP_BLD + p] = __float2half(s);
     const uint32_t mpos = __ballot_sync(0xffffffffu, inb && x > 0.f);
@@ -236,6 +289,24 @@ int postproc_fast_launch(const void* logits, const void* probsT_f16, const float
 
 using namespace psalm;
 
+static int launch_generic(const PostprocArgs& a, bool composed, int dtype, cudaStream_t st) {
+  dim3 grid((a.W + PP_TW - 1) / PP_TW, (a.H + PP_TH - 1) / PP_TH);
+  const size_t smem = pp_smem_bytes();
+  cudaError_t e = cudaSuccess;
+#define PPL(T, C)                                                                                               \
+  e = cudaFuncSetAttribute(postproc_fused_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e == cudaSuccess) postproc_fused_kernel<T, C><<<grid, 256, smem, st>>>(a)
+#define PPD(T) do { if (composed) { PPL(T, true); } else { PPL(T, false); } } while (0)
+  if (dtype == PSALM_F32) PPD(float);
+  else if (dtype == PSALM_F16) PPD(__half);
+  else if (dtype == PSALM_BF16) PPD(__nv_bfloat16);
+  else { set_error("postproc_fused: unknown dtype %d", dtype); return PSALM_E_ARG; }
+#undef PPD
+#undef PPL
+  if (e != cudaSuccess) { set_error("postproc_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSALM_E_CUDA; }
+  return check_launch("postproc_fused_kernel");
+}
+
 static int g_postproc_impl = 0;   // 0 auto, 1 generic SIMT-blend kernel, 2 tensor-core kernel
 
 extern "C" int psalm_set_postproc_impl(int impl) {
@@ -280,19 +351,42 @@ extern "C" int psalm_postproc_fused(const void* logits, const void* probsT_f16, 
   const int SR = (int)(PP_TH * sh) + 3, SC = (int)(PP_TW * sw) + 3;
   PSALM_REQUIRE(SR * SC <= PP_SRC_MAX, "postproc_fused: resize factor too small for the fused path (%dx%d source taps per tile)", SR, SC);
   PostprocArgs a{logits, (const __half*)probsT_f16, wq, negq, slot_query, sem_seg, inst_masks, ids, in_mask, partials,
-                 Q, H4, W4, H, W, ncls, K};
-  dim3 grid((W + PP_TW - 1) / PP_TW, (H + PP_TH - 1) / PP_TH);
-  const size_t smem = pp_smem_bytes();
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaSuccess;
-#define PPL(T)                                                                                          \
-  e = cudaFuncSetAttribute(postproc_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  if (e == cudaSuccess) postproc_fused_kernel<T><<<grid, 256, smem, st>>>(a)
-  if (dtype == PSALM_F32) { PPL(float); }
-  else if (dtype == PSALM_F16) { PPL(__half); }
-  else if (dtype == PSALM_BF16) { PPL(__nv_bfloat16); }
-  else { set_error("postproc_fused: unknown dtype %d", dtype); return PSALM_E_ARG; }
-#undef PPL
-  if (e != cudaSuccess) { set_error("postproc_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSALM_E_CUDA; }
-  return check_launch("postproc_fused_kernel");
+                 Q, H4, W4, H, W, ncls, K, 0, H, W, H, W};
+  return launch_generic(a, false, dtype, (cudaStream_t)stream);
+}
+
+// source taps of one output tile for the composed (up-sample -> crop -> resize) path
+static void composed_window(int H4, int W4, int Hp, int Wp, int oh, int ow, int H, int W, int& SR, int& SC) {
+  const float r2h = (float)oh / (float)H, r2w = (float)ow / (float)W, r1h = (float)H4 / (float)Hp, r1w = (float)W4 / (float)Wp;
+  SR = (int)(((float)PP_TH * r2h + 2.f) * r1h) + 3;
+  SC = (int)(((float)PP_TW * r2w + 2.f) * r1w) + 3;
+}
+
+extern "C" int psalm_postproc_crop_supported(int Q, int H4, int W4, int Hp, int Wp, int oh, int ow, int H, int W, int ncls) {
+  if (Q <= 0 || Q > 104 || ncls > PP_CP || oh <= 0 || ow <= 0 || oh > Hp || ow > Wp || H <= 0 || W <= 0) return 0;
+  int SR, SC;
+  composed_window(H4, W4, Hp, Wp, oh, ow, H, W, SR, SC);
+  return SR * SC <= PP_SRC_MAX ? 1 : 0;
+}
+
+extern "C" int psalm_postproc_crop_partials(int H, int W, int* rows) {
+  PSALM_REQUIRE(rows && H > 0 && W > 0, "postproc_crop_partials: bad arguments");
+  *rows = ((W + PP_TW - 1) / PP_TW) * ((H + PP_TH - 1) / PP_TH);
+  return PSALM_OK;
+}
+
+extern "C" int psalm_postproc_fused_crop(const void* logits, const void* probsT_f16, const float* wq, const float* negq,
+                                         const int* slot_query, float* sem_seg, float* inst_masks, int* ids,
+                                         unsigned char* in_mask, float* partials, int Q, int H4, int W4, int Hp, int Wp,
+                                         int oh, int ow, int H, int W, int ncls, int K, int dtype, void* stream) {
+  PSALM_REQUIRE(logits && partials, "postproc_fused_crop: null pointer");
+  PSALM_REQUIRE((probsT_f16 == nullptr) == (sem_seg == nullptr), "postproc_fused_crop: probsT and sem_seg go together");
+  PSALM_REQUIRE((wq == nullptr) == (ids == nullptr) && (wq == nullptr) == (negq == nullptr) && (wq == nullptr) == (in_mask == nullptr),
+                "postproc_fused_crop: wq / negq / ids / in_mask go together");
+  PSALM_REQUIRE((slot_query == nullptr) == (inst_masks == nullptr), "postproc_fused_crop: slot_query and inst_masks go together");
+  PSALM_REQUIRE(psalm_postproc_crop_supported(Q, H4, W4, Hp, Wp, oh, ow, H, W, ncls),
+                "postproc_fused_crop: unsupported geometry (Q=%d, crop %dx%d of %dx%d -> %dx%d)", Q, oh, ow, Hp, Wp, H, W);
+  PostprocArgs a{logits, (const __half*)probsT_f16, wq, negq, slot_query, sem_seg, inst_masks, ids, in_mask, partials,
+                 Q, H4, W4, H, W, ncls, K, 1, Hp, Wp, oh, ow};
+  return launch_generic(a, true, dtype, (cudaStream_t)stream);
 }

@@ -232,17 +232,26 @@ def group_norm_tokens(x, weight, bias, groups=32, eps=1e-5, relu=False, pre_bias
 
 
 @_on_device
-def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0):
+def postproc_crop_supported(Q, H4, W4, Hp, Wp, oh, ow, H, W, ncls):
+    return bool(_lib.lib().psalm_postproc_crop_supported(Q, H4, W4, Hp, Wp, oh, ow, H, W, ncls))
+
+
+def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0, crop=None):
     """logits [Q,H4,W4] -> dict(sem_seg, ids, in_mask, inst_masks, stats [Q,5]) at output size (H, W).
-    stats columns: count(x>0), sum(sigmoid*[x>0]), count(x>=0), panoptic area, panoptic intersection."""
+    stats columns: count(x>0), sum(sigmoid*[x>0]), count(x>=0), panoptic area, panoptic intersection.
+    crop = (Hp, Wp, oh, ow): up-sample to the padded size (Hp, Wp), crop to (oh, ow), resize to (H, W) (the reference's
+    sem_seg_postprocess flow) composed inside the kernel; None: (H, W) is the up-sampled size itself."""
     import ctypes
     _chk(logits, "postproc_fused.logits")
     Q, H4, W4 = logits.shape
     dev = logits.device
     K = 0 if slot_query is None else slot_query.shape[0]
     rows = ctypes.c_int()
-    _lib.check(_lib.lib().psalm_postproc_partials(Q, H4, W4, H, W, ncls, K, _lib.dtype_code(logits.dtype), ctypes.byref(rows)),
-               "psalm_postproc_partials")
+    if crop is not None:
+        _lib.check(_lib.lib().psalm_postproc_crop_partials(H, W, ctypes.byref(rows)), "psalm_postproc_crop_partials")
+    else:
+        _lib.check(_lib.lib().psalm_postproc_partials(Q, H4, W4, H, W, ncls, K, _lib.dtype_code(logits.dtype), ctypes.byref(rows)),
+                   "psalm_postproc_partials")
     partials = torch.empty((rows.value, Q, 5), dtype=torch.float32, device=dev)
     out = {}
     sem = ids = inm = inst = None
@@ -259,9 +268,15 @@ def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=Non
         K = slot_query.shape[0]
         inst = torch.empty((K, H, W), dtype=torch.float32, device=dev)
     p = lambda t: _lib.ptr(t) if t is not None else None  # noqa: E731
-    rc = _lib.lib().psalm_postproc_fused(p(logits), p(probsT), p(wq), p(negq), p(slot_query), p(sem), p(inst), p(ids),
-                                         p(inm), p(partials), Q, H4, W4, H, W, ncls, K, _lib.dtype_code(logits.dtype),
-                                         _lib.stream_ptr(dev))
+    if crop is not None:
+        Hp, Wp, oh, ow = crop
+        rc = _lib.lib().psalm_postproc_fused_crop(p(logits), p(probsT), p(wq), p(negq), p(slot_query), p(sem), p(inst), p(ids),
+                                                  p(inm), p(partials), Q, H4, W4, Hp, Wp, oh, ow, H, W, ncls, K,
+                                                  _lib.dtype_code(logits.dtype), _lib.stream_ptr(dev))
+    else:
+        rc = _lib.lib().psalm_postproc_fused(p(logits), p(probsT), p(wq), p(negq), p(slot_query), p(sem), p(inst), p(ids),
+                                             p(inm), p(partials), Q, H4, W4, H, W, ncls, K, _lib.dtype_code(logits.dtype),
+                                             _lib.stream_ptr(dev))
     _lib.check(rc, "psalm_postproc_fused")
     _count()
     out.update(sem_seg=sem, ids=ids, in_mask=inm, inst_masks=inst, stats=partials.sum(0))

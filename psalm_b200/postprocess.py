@@ -146,7 +146,7 @@ def thing_tensor(is_thing_list, device):
 
 
 def fused_device(kernels, logits, H, W, cls=None, SEG_cls=None, thing=None, semantic_on=False, instance_on=False,
-                 panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8):
+                 panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8, crop=None):
     """Device part of the fused task heads (no host synchronisation, CUDA-graph capturable): small
     [Q, n_cls] tensor algebra in torch + ONE fused kernel (csrc/postproc.cu) on the LOW-RESOLUTION mask
     logits [Q,H4,W4].  Returns device tensors plus `hostvec`, the one vector the host part needs."""
@@ -182,7 +182,7 @@ def fused_device(kernels, logits, H, W, cls=None, SEG_cls=None, thing=None, sema
         s, qi = torch.sigmoid(SEG_cls.float()).flatten(0, 1).topk(topk, sorted=False)
         keep_i = torch.ones_like(qi, dtype=torch.bool)
         slots = qi.to(torch.int32).contiguous()
-    k = kernels.postproc_fused(logits.contiguous(), H, W, probsT, wq, negq, slots, ncls)
+    k = kernels.postproc_fused(logits.contiguous(), H, W, probsT, wq, negq, slots, ncls, crop=crop)
     st = k["stats"]
     d.update(sem_seg=k["sem_seg"], inst_masks=k["inst_masks"], ids=k["ids"], in_mask=k["in_mask"], lab=lab, qi=qi)
     rows = []
@@ -247,10 +247,10 @@ def fused_host(d, is_thing_list=None, ovl_thr=0.8):
 
 
 def fused_postprocess(kernels, logits, H, W, cls=None, SEG_cls=None, is_thing_list=None, semantic_on=False,
-                      instance_on=False, panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8, ovl_thr=0.8):
+                      instance_on=False, panoptic_on=False, referring_on=False, topk=100, obj_thr=0.8, ovl_thr=0.8, crop=None):
     """All task heads of one image from the LOW-RESOLUTION mask logits with one fused kernel — same results
     as the step-by-step functions above applied to the up-sampled [Q,H,W] map, which is never materialised."""
     thing = thing_tensor(is_thing_list, logits.device) if (panoptic_on and instance_on) else None
     d = fused_device(kernels, logits, H, W, cls, SEG_cls, thing, semantic_on, instance_on, panoptic_on, referring_on,
-                     topk, obj_thr)
+                     topk, obj_thr, crop=crop)
     return fused_host(d, is_thing_list, ovl_thr)

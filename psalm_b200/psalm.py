@@ -223,8 +223,9 @@ class PSALM:
         return out
 
     # ---- CUDA-graph replay of the device-only part -------------------------------------------------
-    def _post_device(self, out, image_hw):
-        """Device part of the fused post-processing for every image (capturable); None if not applicable."""
+    def _post_device(self, out, image_hw, geoms=None):
+        """Device part of the fused post-processing for every image (capturable); None if not applicable.
+        geoms: per image (oh, ow, height, width) = un-padded box and output size; None = no crop, output = padded size."""
         Hi, Wi = image_hw
         d = self.size_divisibility
         Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d
@@ -237,19 +238,26 @@ class PSALM:
         from . import kernels
         thing = PP.thing_tensor(self.is_thing_list, self.device) if (self.panoptic_on and self.instance_on) else None
         pm = out["pred_masks"].view(B, Q, H4, W4)
-        return [PP.fused_device(kernels, pm[b], Hp, Wp, cls[b] if cls is not None else None,
-                                out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None, thing,
-                                self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
-                                self.test_topk_per_image, self.object_mask_threshold) for b in range(B)]
+        res = []
+        for b in range(B):
+            oh, ow, height, width = geoms[b] if geoms is not None else (Hp, Wp, Hp, Wp)
+            crop = None if (oh, ow, height, width) == (Hp, Wp, Hp, Wp) else (Hp, Wp, oh, ow)
+            res.append(PP.fused_device(kernels, pm[b], height, width, cls[b] if cls is not None else None,
+                                       out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None, thing,
+                                       self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
+                                       self.test_topk_per_image, self.object_mask_threshold, crop=crop))
+        return res
 
     MAX_GRAPHS = 8   # each entry owns static buffers + a private pool (hundreds of MB at 1024^2, B = 4)
 
     def forward_core_graphed(self, images, plan, lane=0, fuse_post=True):
+        # fuse_post: True (no crop / resize), False (task heads outside the graph) or a tuple of per-image geometries
         """Same results as forward_core, replayed from a CUDA graph captured per (image size, prompt
         structure): the ~800 launches of one image become one graph launch (the reference issues them
         one by one from Python, plus ~150 extra tiny launches in its decoder).  `lane` selects an
         independent graph + static buffers so that several images can be in flight on different streams."""
-        key = (lane, bool(fuse_post), self.seg_task, float(self.object_mask_threshold), tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), str(images.dtype), plan.B,
+        geoms = fuse_post if isinstance(fuse_post, tuple) else None
+        key = (lane, fuse_post, self.seg_task, float(self.object_mask_threshold), tuple(getattr(self, "is_thing_list", None) or ()), tuple(images.shape), str(images.dtype), plan.B,
                plan.T, plan.n_img, plan.any_padding,
                None if plan.cls_pool is None else tuple(plan.cls_pool.shape), plan.refer_pool is not None,
                None if plan.pad_pos is None else int(plan.pad_pos.numel()))
@@ -272,14 +280,15 @@ class PSALM:
             with torch.cuda.stream(side):
                 for _ in range(2):
                     o = self.forward_core(static_img, static_plan)
-                    o["post"] = self._post_device(o, hw) if fuse_post else None
+                    o["post"] = self._post_device(o, hw, geoms) if fuse_post else None
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with self._precision_scope(), torch.cuda.graph(g):
                 static_out = self._forward_core(static_img, static_plan)
                 # task heads' device part in the same graph (only when every image takes the fused path)
-                static_out["post"] = self._post_device(static_out, hw) if fuse_post else None
+                static_out["post"] = self._post_device(static_out, hw, geoms) if fuse_post else None
+                static_out["post_geoms"] = geoms
             ent = (g, static_img, static_plan, static_out)
             while len(self._graphs) >= self.MAX_GRAPHS:   # least recently used graph and its static buffers go
                 self._graphs.popitem(last=False)
@@ -380,15 +389,26 @@ class PSALM:
         return self.post_process(out, images.shape[-2:], seg_info, boxes)
 
     def _fused_applies(self, image_hw, seg_info):
-        """True when every image of the batch takes the fused task-head kernel (no crop, output size == padded
-        input size); otherwise the graph is captured without the fused kernel instead of running it for nothing."""
+        """(fuse_post, boxes): fuse_post is True when every image takes the fused task-head kernel without crop / resize,
+        a tuple of per-image (oh, ow, height, width) when the composed up-sample -> crop -> resize kernel applies to all of
+        them (the reference's mapper flow: padded 1024^2 input, original-size output), False otherwise (the graph is then
+        captured without the task heads instead of running them for nothing)."""
         Hi, Wi = image_hw
         d = self.size_divisibility
         Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d
         boxes = [PP.unpadded_box(info["padding_mask"]) for info in seg_info]
-        fused = all((info.get("height", Hi), info.get("width", Wi)) == (Hp, Wp) and box == (Hp, Wp)
-                    for info, box in zip(seg_info, boxes))
-        return fused, boxes
+        geoms = tuple((box[0], box[1], info.get("height", Hi), info.get("width", Wi)) for info, box in zip(seg_info, boxes))
+        if all(g == (Hp, Wp, Hp, Wp) for g in geoms):
+            return True, boxes
+        if not (self.fused_postprocess and self.sem_seg_postprocess_before_inference):
+            return False, boxes
+        from . import kernels
+        ps = self.cfg.swin.patch
+        H4, W4 = -(-Hi // ps), -(-Wi // ps)
+        ncls = 144
+        ok = all(kernels.postproc_crop_supported(self.num_queries, H4, W4, Hp, Wp, g[0], g[1], g[2], g[3], ncls) or
+                 g == (Hp, Wp, Hp, Wp) for g in geoms) and self.num_queries <= 104 and Hp >= 2 * H4 and Wp >= 2 * W4
+        return (geoms if ok else False), boxes
 
     @torch.no_grad()
     def post_process(self, out, image_hw, seg_info, boxes=None):
@@ -413,10 +433,20 @@ class PSALM:
             cls_b = out["pred_class_name_logits"][b] if out["pred_class_name_logits"] is not None else None
             seg_b = out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None
             trivial = (oh, ow) == (Hp, Wp) and (height, width) == (Hp, Wp)
-            if trivial and out.get("post") is not None:
+            pg = out.get("post_geoms")
+            if out.get("post") is not None and ((pg is None and trivial) or (pg is not None and pg[b] == (oh, ow, height, width))):
                 results.append(PP.fused_host(out["post"][b], getattr(self, "is_thing_list", None),
                                              self.overlap_threshold))
                 continue
+            if (not trivial and self.fused_postprocess and self.sem_seg_postprocess_before_inference and Q <= 104 and
+                    Hp >= 2 * H4 and Wp >= 2 * W4 and (cls_b is None or cls_b.shape[-1] - 1 <= 144)):
+                from . import kernels
+                if kernels.postproc_crop_supported(Q, H4, W4, Hp, Wp, oh, ow, height, width, 144):
+                    results.append(PP.fused_postprocess(
+                        kernels, pm[b], height, width, cls_b, seg_b, getattr(self, "is_thing_list", None), self.semantic_on,
+                        self.instance_on, self.panoptic_on, self.referring_on, self.test_topk_per_image,
+                        self.object_mask_threshold, self.overlap_threshold, crop=(Hp, Wp, oh, ow)))
+                    continue
             if self.fused_postprocess and trivial and Hp >= 2 * H4 and Wp >= 2 * W4 and Q <= 104 and \
                     (cls_b is None or cls_b.shape[-1] - 1 <= 144):
                 from . import kernels

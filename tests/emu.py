@@ -180,10 +180,19 @@ def install(monkeypatch):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 
-def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0):
+def postproc_crop_supported(*a):
+    return True
+
+
+def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=None, ncls=0, crop=None):
     """torch restatement of csrc/postproc.cu (one tile = the whole image)."""
     Q = logits.shape[0]
-    x = F.interpolate(logits.float()[None], size=(H, W), mode="bilinear", align_corners=False)[0]
+    if crop is not None:   # up-sample to the padded size, crop, resize (sem_seg_postprocess)
+        Hp, Wp, oh, ow = crop
+        x = F.interpolate(logits.float()[None], size=(Hp, Wp), mode="bilinear", align_corners=False)[:, :, :oh, :ow]
+        x = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=False)[0]
+    else:
+        x = F.interpolate(logits.float()[None], size=(H, W), mode="bilinear", align_corners=False)[0]
     s = torch.sigmoid(x)
     out = dict(sem_seg=None, ids=None, in_mask=None, inst_masks=None)
     stats = torch.zeros(Q, 5)

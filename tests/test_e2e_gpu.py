@@ -236,3 +236,40 @@ def test_baseline_configs_full_size_bf16(task, H, W, ncls, batch):
             pan, info = a["panoptic_seg"]
             assert tuple(pan.shape) == (H, W) and torch.equal(pan, b["panoptic_seg"][0]) and info == b["panoptic_seg"][1]
             assert set(np.unique(pan.cpu().numpy()).tolist()) <= set([0] + [d["id"] for d in info])
+
+
+def test_mapper_flow_uses_the_fused_kernel_and_matches_the_oracle(monkeypatch):
+    """The reference's real eval flow (coco_panoptic_mapper.py:148-162): image resized + padded to a square with a
+    padding mask, outputs at the ORIGINAL size.  16-bit runs take the composed fused kernel (eager and CUDA graph), whose
+    results must equal the step-by-step torch path on the same mask logits and track the fp32 oracle."""
+    from psalm_b200 import postprocess as PP
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=21)
+    inp = synth.synth_inputs(batch=2, height=256, width=256, task="panoptic", n_classes=9, seed=22)
+    pm = torch.zeros(256, 256, dtype=torch.bool)
+    pm[192:, :] = True                       # a 4:3 image resized to 256 x 192, padded at the bottom
+    inp["seg_info"] = [dict(padding_mask=pm, height=120, width=160), dict(padding_mask=pm.clone(), height=300, width=400)]
+    ores, it = _oracle(sd, inp, "panoptic")
+    calls = []
+    real = PP.fused_device
+
+    def spy(*a, **k):
+        calls.append(k.get("crop"))
+        return real(*a, **k)
+    monkeypatch.setattr(PP, "fused_device", spy)
+    outs = {}
+    for graph in (False, True):
+        m = PSALM(sd, SMALL, torch.bfloat16, "cuda", "panoptic", use_cuda_graph=graph)
+        m.object_mask_threshold = m.overlap_threshold = 0.0      # keep segments on random weights
+        res = _eval(m, inp)
+        res = _eval(m, inp)
+        outs[graph] = res
+        for b, (hh, ww) in enumerate(((120, 160), (300, 400))):
+            assert tuple(res[b]["sem_seg"].shape) == (8, hh, ww) and tuple(res[b]["panoptic_seg"][0].shape) == (hh, ww)
+            assert res[b]["instances"].pred_masks.shape[1:] == (hh, ww)
+            a, o = res[b]["sem_seg"].float().cpu(), ores[b]["sem_seg"]
+            assert (a - o).norm() / o.norm() < 0.2
+    assert calls and all(c == (256, 256, 192, 256) for c in calls)          # the composed kernel ran, never the slow path
+    for b in range(2):                                                       # graph replay == eager
+        assert torch.equal(outs[False][b]["panoptic_seg"][0], outs[True][b]["panoptic_seg"][0])
+        assert torch.equal(outs[False][b]["sem_seg"], outs[True][b]["sem_seg"])

@@ -157,3 +157,45 @@ def test_tensor_core_path_forced_unsupported_raises():
             kernels.postproc_fused(logits, 61, 85)
     finally:
         _set_impl(0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("geom", [(64, 64, 256, 256, 192, 256, 120, 160), (48, 64, 192, 256, 150, 200, 300, 400),
+                                  (64, 64, 256, 256, 256, 171, 640, 427), (40, 40, 160, 160, 160, 160, 160, 160),
+                                  (256, 256, 1024, 1024, 768, 1024, 480, 640)],
+                         ids=["down", "up", "portrait", "identity", "coco-1024"])
+def test_composed_crop_resize_kernel(dt, geom):
+    """The reference's eval flow - up-sample to the padded size, crop to the un-padded box, resize to the original size
+    (sem_seg_postprocess inside eval_seg, llava_phi.py:1399-1430) - composed inside the fused kernel, against the torch
+    restatement that materialises both intermediates."""
+    from psalm_b200 import kernels
+    H4, W4, Hp, Wp, oh, ow, H, W = geom
+    Q, ncls = 100, 133
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(Q, H4, W4, generator=g) * 4).to(dt)
+    probs = F.softmax(torch.randn(Q, ncls + 1, generator=g) * 3, -1)[:, :-1]
+    probsT = torch.zeros(144, 112, dtype=torch.float16)
+    probsT[:ncls, :Q] = probs.t().half()
+    keep = torch.rand(Q, generator=g) > 0.5
+    wq = torch.where(keep, torch.rand(Q, generator=g), torch.zeros(Q))
+    negq = keep.float() - 1
+    slots = torch.randint(-1, Q, (100,), generator=g).to(torch.int32)
+    assert kernels.postproc_crop_supported(Q, H4, W4, Hp, Wp, oh, ow, H, W, ncls)
+    ref = emu.postproc_fused(logits, H, W, probsT, wq, negq, slots, ncls, crop=(Hp, Wp, oh, ow))
+    o = kernels.postproc_fused(logits.cuda(), H, W, probsT.cuda(), wq.cuda(), negq.cuda(), slots.cuda(), ncls, crop=(Hp, Wp, oh, ow))
+    torch.cuda.synchronize()
+    x = F.interpolate(F.interpolate(logits.float()[None], size=(Hp, Wp), mode="bilinear", align_corners=False)[:, :, :oh, :ow],
+                      size=(H, W), mode="bilinear", align_corners=False)[0]
+    near = (x.abs() < 1e-4)
+    slack = near.flatten(1).sum(1).float()
+    st = o["stats"].cpu()
+    assert ((st[:, 0] - ref["stats"][:, 0]).abs() <= slack).all()
+    assert ((st[:, 2] - ref["stats"][:, 2]).abs() <= slack).all()
+    assert torch.allclose(st[:, 1], ref["stats"][:, 1], rtol=2e-3, atol=5e-2)
+    assert (o["sem_seg"].cpu() - ref["sem_seg"]).abs().max() / ref["sem_seg"].abs().max() < 2e-3
+    assert (o["ids"].cpu() != ref["ids"]).float().mean() < 2e-4
+    assert torch.equal(st[:, 3].sum(), torch.tensor(float(H * W)))
+    valid = slots >= 0
+    bad = (o["inst_masks"].cpu()[valid] != ref["inst_masks"][valid]).flatten(1).sum(1).float()
+    assert (bad <= slack[slots[valid].long()]).all()
