@@ -101,7 +101,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-MSDA_KERNEL = "msda_encoder_fused_kernel"
+MSDA_KERNEL = "msda_encoder_fused_kernel"   # the L1-gather kernel (auto); the TMA-tile kernel (impl 3) is slower, DESIGN.md
 
 
 def msda_traffic(B, dtype):
@@ -313,6 +313,22 @@ def run_ours(args, rank, world, local_rank):
         ms1 = PD.max_over_ranks([timed_device_steps(step_b1, K, W, barrier)], dev)[0]
         b1 = {"value": K * world * 100.0 / (ms1 / 1e3), "unit": "masks/s", "ms_per_image": ms1 / K, "batch_per_gpu": 1}
 
+    # the reference's real eval flow (coco_panoptic_mapper.py:148-162): a 640 x 480 image resized to 1024 x 768, padded to
+    # 1024^2 with a padding mask, outputs at the original size - the composed fused task-head kernel (crop + resize)
+    mflow = None
+    if not args.no_graph and not args.no_batch1:
+        pmask = torch.zeros(IMG, IMG, dtype=torch.bool)
+        pmask[768:, :] = True
+        seg_m = [dict(padding_mask=pmask, height=480, width=640) for _ in range(B)]
+        fused_m, boxes_m = model._fused_applies((IMG, IMG), seg_m)
+
+        def step_mapper():
+            out = model.forward_core_graphed(images_d, plan_d, fuse_post=fused_m)
+            return model.post_process(out, (IMG, IMG), seg_m, boxes_m)
+        msm = PD.max_over_ranks([timed_device_steps(step_mapper, K, W, barrier)], dev)[0]
+        mflow = {"value": K * B * world * 100.0 / (msm / 1e3), "unit": "masks/s", "ms_per_step": msm / K,
+                 "fused_task_heads": bool(fused_m), "geometry": "1024x768 valid region of the padded 1024^2 input -> 480x640 outputs"}
+
     # roofline leg: the same K steps launched eagerly (a CUDA graph cannot carry timing events), with
     # CUDA events on the launch stream around every hot-kernel launch; also counts our launches per step
     def step_eager():
@@ -466,6 +482,8 @@ def run_ours(args, rank, world, local_rank):
             "wall_s": time.perf_counter() - wall0}
     if b1 is not None:
         line["batch1"] = b1
+    if mflow is not None:
+        line["mapper_flow"] = mflow
     if parity_line is not None:
         line["parity"] = parity_line
     if accuracy_line is not None:
