@@ -365,37 +365,77 @@ def run_ours(args, rank, world, local_rank):
     # per step: uint8 image batch uploaded from pinned memory on the copy stream (the upload of step k+1 overlaps the
     # compute of step k), normalisation on the device, eval_seg, results read back to the host, and (N > 1) the
     # all_gather of every rank's predictions - all inside the timed region
-    def step_e2e(staged):
-        res = model.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=staged,
-                             seg_info=inp["seg_info"], **kw)
-        meta, maps = PD.pack_predictions(res, model.num_queries)
-        gmeta, gmaps = PD.gather_predictions(meta, maps)          # NCCL all_gather over NVLink (no-op at N = 1)
-        host = [gmeta.cpu(), gmaps.cpu()]
-        host += [r["sem_seg"].argmax(0).to(torch.uint8).cpu() for r in res]
+    # Pipelined through the public async API: batch k+1 is submitted (lane (k+1) % 2) before batch k is finished, and
+    # the finish work of k (host merge of the panoptic rule, id maps, packing, all_gather, read-back into pinned
+    # buffers) runs on a side stream under the device work of k+1.  Every batch is fully read back; the clock
+    # stops after the last one.
+    post_stream = torch.cuda.Stream(device=dev)
+    pins = {}
+
+    def to_pinned(name, t):
+        buf = pins.get(name)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = pins[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def submit(k, staged):
+        return model.eval_seg_async(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=staged,
+                                    seg_info=inp["seg_info"], lane=k % 2, **kw)
+
+    def finish(pending):
+        with torch.cuda.stream(post_stream):
+            res = pending.result()
+            meta, maps = PD.pack_predictions(res, model.num_queries)
+            gmeta, gmaps = PD.gather_predictions(meta, maps)      # NCCL all_gather over NVLink (no-op at N = 1)
+            host = [to_pinned("meta", gmeta), to_pinned("maps", gmaps)]
+            sem = torch.stack([r["sem_seg"].argmax(0).to(torch.uint8) for r in res])
+            host.append(to_pinned("sem", sem))
+        post_stream.synchronize()
         return host
 
     def run_e2e(n):
-        nxt = model.stage_images(images_u8_h)
         host = None
+        pend = submit(0, model.stage_images(images_u8_h))
+        for k in range(n):
+            nxt = submit(k + 1, model.stage_images(images_u8_h)) if k + 1 < n else None
+            host = finish(pend)
+            pend = nxt
+        return host
+
+    def run_e2e_sync(n):     # the blocking call, one batch at a time (what round 1 reported as e2e)
+        host = None
+        nxt = model.stage_images(images_u8_h)
         for k in range(n):
             cur = nxt
             if k + 1 < n:
                 nxt = model.stage_images(images_u8_h)
-            host = step_e2e(cur)
+            res = model.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=cur,
+                                 seg_info=inp["seg_info"], **kw)
+            meta, maps = PD.pack_predictions(res, model.num_queries)
+            gmeta, gmaps = PD.gather_predictions(meta, maps)
+            host = [to_pinned("meta", gmeta), to_pinned("maps", gmaps),
+                    to_pinned("sem", torch.stack([r["sem_seg"].argmax(0).to(torch.uint8) for r in res]))]
+            torch.cuda.synchronize()
         return host
 
-    run_e2e(2)
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    host = run_e2e(K)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    def timed_wall(fn):
+        fn(3)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        host = fn(K)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return host, dt
+
+    host, e2e_sync_s = timed_wall(run_e2e_sync)
+    host, e2e_s = timed_wall(run_e2e)
     h2d = images_u8_h.numel() * images_u8_h.element_size()
     d2h = sum(t.numel() * t.element_size() for t in host)
     nvlink = 0 if world == 1 else (host[0].numel() * 4 + host[1].numel() * 4)
-    ms_total, e2e_ms = PD.max_over_ranks([ms_total, e2e_s * 1e3], dev)
+    ms_total, e2e_ms, e2e_sync_ms = PD.max_over_ranks([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3], dev)
 
     # ---------------- parity + accuracy vs the CPU oracle (checker only; outside every timed region) -------------
     parity_line = accuracy_line = cpu_line = None
@@ -470,7 +510,11 @@ def run_ours(args, rank, world, local_rank):
                        "e2e_input": "uint8 [B,3,1024,1024] from pinned host memory, normalised on the device; upload of "
                                     "step k+1 overlaps compute of step k; results + (N>1) prediction all_gather inside"},
             "e2e": {"value": e2e_value, "unit": "masks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / K, "nvlink_gather_bytes_per_step": int(nvlink)},
+                    "ms_per_step": e2e_ms / K, "nvlink_gather_bytes_per_step": int(nvlink),
+                    "api": "PSALM.eval_seg_async, two lanes: batch k is finished (host merge, gather, read-back to pinned "
+                           "memory) under the device work of batch k+1",
+                    "blocking_call": {"value": images_total * 100.0 / (e2e_sync_ms / 1e3), "ms_per_step": e2e_sync_ms / K,
+                                      "api": "PSALM.eval_seg, one batch at a time"}},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // K),
             "clocks": clocks,
             "roofline": dict({"kernel": MSDA_KERNEL, "bound": "hbm", "achieved": achieved, "peak": hbm,

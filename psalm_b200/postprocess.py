@@ -196,14 +196,15 @@ def fused_device(kernels, logits, H, W, cls=None, SEG_cls=None, thing=None, sema
     return d
 
 
-def fused_host(d, is_thing_list=None, ovl_thr=0.8):
+def fused_host(d, is_thing_list=None, ovl_thr=0.8, host=None):
     """Host part: the ONE D2H copy, the sequential panoptic merge rule on <= Q integers
     (llava_phi.py:355-384) and the final id lookup."""
     Q, H, W = d["Q"], d["H"], d["W"]
     r = {}
     if d["has_sem"]:
         r["sem_seg"] = d["sem_seg"]
-    host = d["hostvec"].cpu().numpy() if d["hostvec"] is not None else None        # the one D2H copy
+    if host is None:   # (else: already copied into pinned memory behind the pass, PSALM.eval_seg_async)
+        host = d["hostvec"].cpu().numpy() if d["hostvec"] is not None else None    # the one D2H copy
     pos = 0
     if d["has_inst"]:
         n_inst = int(host[0])

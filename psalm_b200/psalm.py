@@ -45,6 +45,30 @@ class StagedImages:
         self.shape, self.dtype = slot[0].shape, slot[0].dtype
 
 
+class PendingSeg:
+    """Handle of a submitted `PSALM.eval_seg_async` call: the network + the device part of the task heads are queued
+    (one graph replay), the few integers the host merge needs are on their way to pinned memory.  `result()` finishes
+    the post-processing ON THE CALLER'S CURRENT STREAM (after making it wait for the pass), so a caller that wants the
+    host work of image batch k to overlap the device work of batch k+1 submits k+1 first and calls `result()` of k
+    under a side stream.  The tensors of the result live in the lane's static buffers: they stay valid until the next
+    submission on the same lane."""
+
+    def __init__(self, model, out, image_hw, seg_info, boxes, done, hostvecs, thing_list, thresholds):
+        self.model, self.out, self.image_hw, self.seg_info, self.boxes = model, out, image_hw, seg_info, boxes
+        self.done, self.hostvecs, self.thing_list, self.thresholds = done, hostvecs, thing_list, thresholds
+
+    def result(self):
+        m = self.model
+        torch.cuda.current_stream(m.device).wait_event(self.done)
+        self.done.synchronize()                              # pinned host vectors are complete
+        keep = (getattr(m, "is_thing_list", None), m.object_mask_threshold, m.overlap_threshold)
+        m.is_thing_list, (m.object_mask_threshold, m.overlap_threshold) = self.thing_list, self.thresholds
+        try:
+            return m.post_process(self.out, self.image_hw, self.seg_info, self.boxes, hostvecs=self.hostvecs)
+        finally:
+            m.is_thing_list, m.object_mask_threshold, m.overlap_threshold = keep
+
+
 class PSALMModel:
     """`model.model` of the reference (PSALMModel(LlavaMetaModel, PhiModel), llava_phi.py:52): owns the
     LLM, the vision tower and the projector."""
@@ -368,6 +392,21 @@ class PSALM:
         if self.panoptic_on:
             assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
             self.is_thing_list = is_thing_list
+        return self.eval_seg_async(input_ids=input_ids, attention_mask=attention_mask, images=images, seg_info=seg_info,
+                                   class_name_ids=class_name_ids, class_name_embedding_indices=class_name_embedding_indices,
+                                   cls_indices=cls_indices, token_refer_id=token_refer_id,
+                                   refer_embedding_indices=refer_embedding_indices, is_thing_list=is_thing_list).result()
+
+    @torch.no_grad()
+    def eval_seg_async(self, input_ids=None, attention_mask=None, images=None, seg_info=None, class_name_ids=None,
+                       class_name_embedding_indices=None, cls_indices=None, token_refer_id=None,
+                       refer_embedding_indices=None, is_thing_list=None, lane=0):
+        """Submit one `eval_seg` call and return a `PendingSeg`; `.result()` gives what `eval_seg` returns.  `lane`
+        selects an independent CUDA graph + static output buffers, so that a caller alternating lanes 0 / 1 can finish
+        batch k (host merge, read-back) while the device already runs batch k+1."""
+        if self.panoptic_on:
+            assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
+            self.is_thing_list = is_thing_list
         staged = images if isinstance(images, StagedImages) else None
         if staged is not None:   # upload already in flight on the copy stream (stage_images)
             torch.cuda.current_stream(self.device).wait_event(staged.ready)
@@ -380,13 +419,33 @@ class PSALM:
                                  class_name_embedding_indices, token_refer_id, refer_embedding_indices)
         fused, boxes = self._fused_applies(images.shape[-2:], seg_info)
         if self.use_cuda_graph:
-            out = self.forward_core_graphed(images_d, plan, fuse_post=fused)
+            out = self.forward_core_graphed(images_d, plan, lane=lane, fuse_post=fused)
         else:
             out = self.forward_core(images_d, plan)
+        cur = torch.cuda.current_stream(self.device)
         if staged is not None:   # the staging buffer may be overwritten once this pass has read it
             staged.slot[1] = torch.cuda.Event()
-            staged.slot[1].record(torch.cuda.current_stream(self.device))
-        return self.post_process(out, images.shape[-2:], seg_info, boxes)
+            staged.slot[1].record(cur)
+        hostvecs = None
+        if out.get("post") is not None:   # the integers of the host merge: device -> pinned memory, behind the pass
+            if not hasattr(self, "_hostvec_pins"):
+                self._hostvec_pins = {}
+            hostvecs = []
+            for b, d in enumerate(out["post"]):
+                hv = d["hostvec"]
+                if hv is None:
+                    hostvecs.append(None)
+                    continue
+                k = (lane, b, tuple(hv.shape), hv.dtype)
+                pin = self._hostvec_pins.get(k)
+                if pin is None:
+                    pin = self._hostvec_pins[k] = torch.empty(hv.shape, dtype=hv.dtype, pin_memory=True)
+                pin.copy_(hv, non_blocking=True)
+                hostvecs.append(pin)
+        done = torch.cuda.Event()
+        done.record(cur)
+        return PendingSeg(self, out, tuple(images.shape[-2:]), seg_info, boxes, done, hostvecs,
+                          getattr(self, "is_thing_list", None), (self.object_mask_threshold, self.overlap_threshold))
 
     def _fused_applies(self, image_hw, seg_info):
         """(fuse_post, boxes): fuse_post is True when every image takes the fused task-head kernel without crop / resize,
@@ -411,13 +470,14 @@ class PSALM:
         return (geoms if ok else False), boxes
 
     @torch.no_grad()
-    def post_process(self, out, image_hw, seg_info, boxes=None):
+    def post_process(self, out, image_hw, seg_info, boxes=None, hostvecs=None):
         """llava_phi.py:1395-1472 for EVERY image of the batch.  `boxes`: un-padded (h, w) per image when the
-        caller already derived them from the padding masks."""
+        caller already derived them from the padding masks; `hostvecs`: the fused heads' host vectors when they were
+        already copied to (pinned) host memory."""
         with self._precision_scope():
-            return self._post_process(out, image_hw, seg_info, boxes)
+            return self._post_process(out, image_hw, seg_info, boxes, hostvecs)
 
-    def _post_process(self, out, image_hw, seg_info, boxes=None):
+    def _post_process(self, out, image_hw, seg_info, boxes=None, hostvecs=None):
         Hi, Wi = image_hw
         d = self.size_divisibility
         Hp, Wp = (Hi + d - 1) // d * d, (Wi + d - 1) // d * d     # ImageList.from_tensors(images, 32), :1400
@@ -435,8 +495,8 @@ class PSALM:
             trivial = (oh, ow) == (Hp, Wp) and (height, width) == (Hp, Wp)
             pg = out.get("post_geoms")
             if out.get("post") is not None and ((pg is None and trivial) or (pg is not None and pg[b] == (oh, ow, height, width))):
-                results.append(PP.fused_host(out["post"][b], getattr(self, "is_thing_list", None),
-                                             self.overlap_threshold))
+                results.append(PP.fused_host(out["post"][b], getattr(self, "is_thing_list", None), self.overlap_threshold,
+                                             host=None if hostvecs is None or hostvecs[b] is None else hostvecs[b].numpy()))
                 continue
             if (not trivial and self.fused_postprocess and self.sem_seg_postprocess_before_inference and Q <= 104 and
                     Hp >= 2 * H4 and Wp >= 2 * W4 and (cls_b is None or cls_b.shape[-1] - 1 <= 144)):

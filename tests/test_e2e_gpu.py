@@ -273,3 +273,39 @@ def test_mapper_flow_uses_the_fused_kernel_and_matches_the_oracle(monkeypatch):
     for b in range(2):                                                       # graph replay == eager
         assert torch.equal(outs[False][b]["panoptic_seg"][0], outs[True][b]["panoptic_seg"][0])
         assert torch.equal(outs[False][b]["sem_seg"], outs[True][b]["sem_seg"])
+
+
+def test_async_two_lane_pipeline_equals_the_blocking_call():
+    """PSALM.eval_seg_async: batch k+1 submitted on the other lane before batch k is finished on a side stream (the
+    pipelined loop bench.py times as e2e) must return exactly what the blocking eval_seg returns for each batch."""
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=31)
+    m = PSALM(sd, SMALL, torch.bfloat16, "cuda", "panoptic", use_cuda_graph=True)
+    m.object_mask_threshold = m.overlap_threshold = 0.0
+    batches = [synth.synth_inputs(batch=2, height=256, width=256, task="panoptic", n_classes=9, seed=40 + i) for i in range(4)]
+    for inp in batches:   # one prompt structure, different images
+        inp.update({k: batches[0][k] for k in batches[0] if k not in ("images", "seg_info")})
+    kw = {k: batches[0][k] for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "is_thing_list")}
+
+    def snap(res):
+        return [(r["panoptic_seg"][0].clone(), [dict(s) for s in r["panoptic_seg"][1]], r["sem_seg"].clone(),
+                 r["instances"].scores.clone(), r["instances"].pred_masks.clone()) for r in res]
+    want = [snap(_eval(m, inp)) for inp in batches]
+    side = torch.cuda.Stream()
+    got = []
+
+    def submit(k):
+        u8 = batches[k]["images"]
+        return m.eval_seg_async(input_ids=batches[k]["input_ids"], attention_mask=batches[k]["attention_mask"],
+                                images=m.stage_images(u8.pin_memory()), seg_info=batches[k]["seg_info"], lane=k % 2, **kw)
+    pend = submit(0)
+    for k in range(len(batches)):
+        nxt = submit(k + 1) if k + 1 < len(batches) else None
+        with torch.cuda.stream(side):
+            got.append(snap(pend.result()))
+        side.synchronize()
+        pend = nxt
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        for (wp, wi, ws, wsc, wm), (gp, gi, gs, gsc, gm) in zip(w, g):
+            assert torch.equal(wp, gp) and wi == gi and torch.equal(ws, gs) and torch.equal(wsc, gsc) and torch.equal(wm, gm)
