@@ -262,6 +262,22 @@ int psalm_paged_decode_attention(const void* q, long long q_batch_stride, const 
 int psalm_patchify(const void* images, void* patches, const float* mean, const float* stdv, int B, int Cin,
                    int H, int W, int patch, int in_dtype, int out_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Linear layer with a fused epilogue (tcgen05 + TMEM accumulators, operands through TMA; csrc/gemm_tc5.cu):
+ *   out = epilogue(a · wᵀ + bias), 16-bit storage (PSALM_BF16 / PSALM_F16), fp32 accumulation.
+ * Replaces the library GEMM + the separate elementwise pass of
+ *   epilogue 1: Swin `Mlp.fc1` followed by the exact-erf `nn.GELU` (multimodal_encoder/swin_trans.py:37-44);
+ *   epilogue 2: MSDeformAttn `value_proj` (ops/modules/ms_deform_attn.py:95-99) stored HEAD-MAJOR
+ *               [M / rows_per_image, N / 32, rows_per_image, 32] - the layout psalm_msda_encoder_fused reads - instead of
+ *               [M, N] followed by a transposing copy;
+ *   epilogue 0: bias only (plain nn.Linear).
+ *   a [M, K] with row stride a_row_stride elements (K contiguous), w [N, K] contiguous (nn.Linear weight), bias [N] or NULL.
+ * Shapes: N % 256 == 0, K % 64 == 0 (psalm_linear_fused_supported returns 1 when the kernel applies).
+ * ------------------------------------------------------------------------------------------ */
+int psalm_linear_fused_supported(long long M, int N, int K, int epilogue, long long rows_per_image, int dtype);
+int psalm_linear_fused(const void* a, long long a_row_stride, const void* w, const void* bias, void* out, long long M, int N,
+                       int K, int epilogue, long long rows_per_image, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -315,6 +315,47 @@ def linear_act(x, weight, bias, act):
     return F.relu(y) if act == "relu" else F.gelu(y, approximate="tanh")
 
 
+LINEAR_FUSED = True   # False: library GEMM + separate elementwise pass (A/B runs)
+_EPILOGUES = {"bias": 0, "gelu_erf": 1, "head_major": 2}
+
+
+def linear_fused_supported(x, weight, epilogue, rows_per_image=0):
+    """True when `linear_fused` applies: 16-bit CUDA tensors, N % 256 == 0, K % 64 == 0."""
+    if not (LINEAR_FUSED and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16)):
+        return False
+    M = x.numel() // x.shape[-1]
+    return bool(_lib.lib().psalm_linear_fused_supported(M, weight.shape[0], weight.shape[1], _EPILOGUES[epilogue],
+                                                        rows_per_image, _lib.dtype_code(x.dtype)))
+
+
+@_on_device
+def linear_fused(x, weight, bias, epilogue, rows_per_image=0):
+    """epilogue(x @ weight.T + bias) on the tcgen05 tensor cores (csrc/gemm_tc5.cu).  x [..., K] (rows contiguous),
+    weight [N, K].  epilogue: "bias", "gelu_erf" (Swin Mlp.fc1 + nn.GELU, swin_trans.py:37-44) or "head_major"
+    (MSDeformAttn value_proj stored [B, N/32, rows_per_image, 32], ms_deform_attn.py:95-99)."""
+    _chk(weight, "linear_fused.weight")
+    if not x.is_cuda:
+        raise _lib.PsalmKernelError("linear_fused.x: expected a CUDA tensor, got %s (no CPU path)" % x.device)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)     # a 2-D row-strided view is consumed in place (TMA row stride)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if epilogue == "head_major":
+        out = torch.empty((M // rows_per_image, N // 32, rows_per_image, 32), dtype=x.dtype, device=x.device)
+    else:
+        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=x.dtype, device=x.device)
+    if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
+        raise _lib.PsalmKernelError("linear_fused: bias must be contiguous and of the storage dtype")
+    rc = _lib.lib().psalm_linear_fused(_lib.ptr(x2), x2.stride(0), _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None,
+                                       _lib.ptr(out), M, N, K, _EPILOGUES[epilogue], rows_per_image,
+                                       _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
+    _lib.check(rc, "psalm_linear_fused")
+    _count()
+    return out
+
+
 @_on_device
 def patchify(images, out_dtype, mean=None, std=None, patch=4):
     """images [B,Cin,H,W] (uint8 / float) -> patches [B, ceil(H/4)*ceil(W/4), Cin*16] in out_dtype, normalised with

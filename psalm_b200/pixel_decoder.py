@@ -133,8 +133,12 @@ class MSDeformAttnPixelDecoder:
             self._pos_ow_cache[pkey] = pos_ow
         for i in range(cfg.enc_layers):
             ow = torch.addmm(pos_ow[i], src.view(B * S, -1), w["e%d.ow.w" % i].t()).view(B, S, -1)
-            value = F.linear(src, w["e%d.vp.w" % i], w["e%d.vp.b" % i])
-            value_hm = value.view(B, S, M, D).permute(0, 2, 1, 3).contiguous()
+            if D == 32 and kernels.linear_fused_supported(src, w["e%d.vp.w" % i], "head_major", S):
+                # value_proj with the head-major store in the GEMM epilogue (csrc/gemm_tc5.cu): no transposing copy
+                value_hm = kernels.linear_fused(src, w["e%d.vp.w" % i], w["e%d.vp.b" % i], "head_major", S)
+            else:
+                value = F.linear(src, w["e%d.vp.w" % i], w["e%d.vp.b" % i])
+                value_hm = value.view(B, S, M, D).permute(0, 2, 1, 3).contiguous()
             a = kernels.timed_msda(kernels.msda_encoder_fused, value_hm, ow.contiguous(), shapes, starts, cfg.enc_points)
             kernels._count()
             src = kernels.add_layer_norm(src, w["e%d.norm1.w" % i], w["e%d.norm1.b" % i],

@@ -112,7 +112,10 @@ class SwinTransformer:
                                   w[p + "rel"], B, Wh, Ww, C, nh, ws, shift)
                 a = F.linear(a, w[p + "attn.proj.w"], w[p + "attn.proj.b"])
                 x, h = LN(x, w[p + "norm2.w"], w[p + "norm2.b"], r1=a, return_sum=True)
-                h = F.gelu(F.linear(h, w[p + "mlp.fc1.w"], w[p + "mlp.fc1.b"]))
+                if kernels.linear_fused_supported(h, w[p + "mlp.fc1.w"], "gelu_erf"):
+                    h = kernels.linear_fused(h, w[p + "mlp.fc1.w"], w[p + "mlp.fc1.b"], "gelu_erf")   # GELU in the epilogue
+                else:
+                    h = F.gelu(F.linear(h, w[p + "mlp.fc1.w"], w[p + "mlp.fc1.b"]))
                 delta = F.linear(h, w[p + "mlp.fc2.w"], w[p + "mlp.fc2.b"])
             x, out = LN(x, w["norm%d.w" % s], w["norm%d.b" % s], r1=delta, return_sum=True)
             outs.append(out)

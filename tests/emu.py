@@ -176,7 +176,7 @@ def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
                  "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify", "masked_cross_attention", "kv_cache_write",
-                 "paged_decode_attention"):
+                 "paged_decode_attention", "linear_fused_supported"):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 
@@ -215,3 +215,7 @@ def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=Non
         out["inst_masks"] = m
     out["stats"] = stats
     return out
+
+
+def linear_fused_supported(*a, **k):
+    return False
