@@ -20,11 +20,12 @@
 // Two accumulators (2 x 256 TMEM columns) so that the MMAs of tile i + 1 run under the epilogue of tile i: at K = 128 the
 // epilogue (32 K GELUs per tile) is the longest stage, not the tensor pipe and not HBM.
 //
-// GELU: 0.5 x (1 + erf(x / sqrt 2)) = x (1 - E / 2) for x > 0, x E / 2 otherwise, E = erfc(|x| / sqrt 2) = 2^q(|x|) with
-// q a degree-8 polynomial fitted to log2 erfc on [0, 5] (clamped beyond: erfc < 2e-12): relative error of the result
-// < 2.5e-5 for |x| < 7, absolute < 1.1e-6 everywhere (checked against float64 erf) - two orders below the 16-bit
-// rounding of the output - at one MUFU and 8 FMAs per element instead of libm's erff.  The result is assembled as
-// max(x, 0) - |x| E / 2 (one FMA), the Horner chain runs two elements at a time on the packed fma.rn.f32x2 pipe.
+// GELU: 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - |x| E / 2 with E = erfc(|x| / sqrt 2); E / 2 = 2^q(t), q a degree-7
+// polynomial fitted to log2(erfc(z) / 2) on z in [0, 5], t = sat(z / 5) (one FMUL.SAT; beyond z = 5, erfc < 2e-12).
+// Relative error of the result < 2.5e-5 for |x| < 7, absolute < 1.5e-6 everywhere (checked against float64 erf, fp32
+// Horner emulated) - two orders below the 16-bit rounding of the output - at one MUFU and 3.5 packed FMAs per element
+// (fma.rn.f32x2) instead of libm's erff.  The first version of this epilogue was issue-bound at Swin stage 0
+// (profiles/r2d_gemm_tc5_*: 13.4 instructions per element, 68 % issue slots busy); this one needs ~9.
 #include <cuda.h>
 
 #include <type_traits>
@@ -39,7 +40,8 @@ constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2, STAGE = A_BYTES + W_
 constexpr int EPI_WARPS = 16, THREADS = (EPI_WARPS + 2) * 32;
 constexpr int EPI_COLS = BN / (EPI_WARPS / 4);   // columns per epilogue warp (4 warps cover the 128 TMEM lanes)
 constexpr int STG_WARP = 32 * EPI_COLS * 2;       // output staging of one epilogue warp: [32 rows x 64 columns] = 4 KB
-constexpr size_t SMEM = 1024 + (size_t)NS * STAGE + (size_t)EPI_WARPS * STG_WARP + 256;
+constexpr int BIAS_WARP = EPI_COLS * 4;           // the warp's bias slice as fp32
+constexpr size_t SMEM = 1024 + (size_t)NS * STAGE + (size_t)EPI_WARPS * (STG_WARP + BIAS_WARP) + 256;
 }  // namespace gt
 
 struct GtParams {
@@ -49,6 +51,7 @@ struct GtParams {
   int epilogue;       // 0 bias, 1 bias + GELU(erf), 2 bias + head-major store [M / S, N / 32, S, 32]
   int S;              // rows per image (epilogue 2)
   int tiles_m, tiles_n;
+  int tn_shift;       // log2(tiles_n) when it is a power of two, else -1
 };
 
 __device__ __forceinline__ uint32_t gt_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,21 +133,26 @@ __device__ __forceinline__ gt_f2 gt_fma2(gt_f2 a, gt_f2 b, gt_f2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
-// GELU of two values; see the header comment.  q(u) ~ log2(erfc(z) / 2), u = 2 z / 5 - 1, z = min(|x| / sqrt 2, 5)
+__device__ __forceinline__ void gt_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ gt_f2 gt_add2(gt_f2 a, gt_f2 b) {
+  gt_f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// GELU of two values; see the header comment.
 __device__ __forceinline__ void gt_gelu2(float& x0, float& x1) {
   const float a0 = fabsf(x0), a1 = fabsf(x1);
-  float u0, u1;
-  gt_unpk(gt_fma2(gt_pk(a0, a1), gt_pk(0.70710678f * 0.4f, 0.70710678f * 0.4f), gt_pk(-1.0f, -1.0f)), u0, u1);
-  const gt_f2 u = gt_pk(fminf(u0, 1.0f), fminf(u1, 1.0f));
-  gt_f2 q = gt_pk(1.750049084e-03f, 1.750049084e-03f);
-  q = gt_fma2(q, u, gt_pk(-1.095149074e-02f, -1.095149074e-02f));
-  q = gt_fma2(q, u, gt_pk(2.956688735e-02f, 2.956688735e-02f));
-  q = gt_fma2(q, u, gt_pk(-6.018700839e-02f, -6.018700839e-02f));
-  q = gt_fma2(q, u, gt_pk(1.210609759e-01f, 1.210609759e-01f));
-  q = gt_fma2(q, u, gt_pk(-2.444154202e-01f, -2.444154202e-01f));
-  q = gt_fma2(q, u, gt_pk(-8.510812522e+00f, -8.510812522e+00f));
-  q = gt_fma2(q, u, gt_pk(-1.930574601e+01f, -1.930574601e+01f));
-  q = gt_fma2(q, u, gt_pk(-1.126285639e+01f - 1.0f, -1.126285639e+01f - 1.0f));   // - 1: the factor 1/2
+  const gt_f2 t = gt_pk(__saturatef(a0 * (0.70710678f * 0.2f)), __saturatef(a1 * (0.70710678f * 0.2f)));
+  gt_f2 q = gt_pk(-1.401790814e+00f, -1.401790814e+00f);
+  q = gt_fma2(q, t, gt_pk(7.022554923e+00f, 7.022554923e+00f));
+  q = gt_fma2(q, t, gt_pk(-1.563424726e+01f, -1.563424726e+01f));
+  q = gt_fma2(q, t, gt_pk(2.078584664e+01f, 2.078584664e+01f));
+  q = gt_fma2(q, t, gt_pk(-1.893136839e+01f, -1.893136839e+01f));
+  q = gt_fma2(q, t, gt_pk(-2.294412836e+01f, -2.294412836e+01f));
+  q = gt_fma2(q, t, gt_pk(-8.139466606e+00f, -8.139466606e+00f));
+  q = gt_fma2(q, t, gt_pk(-1.000004739e+00f, -1.000004739e+00f));
   float q0, q1, h0, h1;
   gt_unpk(q, q0, q1);
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(h0) : "f"(q0));
@@ -153,6 +161,16 @@ __device__ __forceinline__ void gt_gelu2(float& x0, float& x1) {
   x1 = fmaf(-a1, h1, fmaxf(x1, 0.f));
 }
 
+template <typename T>
+__device__ __forceinline__ float2 load_pair_f32(const T* p);
+template <>
+__device__ __forceinline__ float2 load_pair_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <>
+__device__ __forceinline__ float2 load_pair_f32<__half>(const __half* p) {
+  return __half22float2(*reinterpret_cast<const __half2*>(p));
+}
 template <typename T>
 __device__ __forceinline__ uint32_t gt_pack(float a, float b);
 template <>
@@ -174,7 +192,8 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   extern __shared__ unsigned char gt_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gt_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* stg_all = base + (size_t)NS * STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + (size_t)EPI_WARPS * STG_WARP);
+  float* bias_all = reinterpret_cast<float*>(stg_all + (size_t)EPI_WARPS * STG_WARP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + (size_t)EPI_WARPS * (STG_WARP + BIAS_WARP));
   uint64_t* full = bars;               // [NS] TMA landed
   uint64_t* empty = bars + NS;         // [NS] the MMAs reading the stage have retired
   uint64_t* acc_full = bars + 2 * NS;  // [2]  accumulator complete
@@ -210,7 +229,7 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+        const int tm = p.tn_shift >= 0 ? t >> p.tn_shift : t / p.tiles_n, tn = t - tm * p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % NS;
           if (it >= NS) gt_mbar_wait(&empty[s], ((it / NS) - 1) & 1);
@@ -248,9 +267,10 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // ------------------------------------------------ epilogue
     const int q4 = warp & 3, g = warp >> 2;   // TMEM lane quarter (hardware: warp % 4), column group
     unsigned char* stg = stg_all + (size_t)warp * STG_WARP;
+    float* bias_s = bias_all + warp * EPI_COLS;
     uint32_t li = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++li) {
-      const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+      const int tm = p.tn_shift >= 0 ? t >> p.tn_shift : t / p.tiles_n, tn = t - tm * p.tiles_n;
       const int a = li & 1;
       gt_mbar_wait(&acc_full[a], (li >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -259,8 +279,13 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const long long row0 = (long long)tm * BM + q4 * 32;      // first row of this warp's box
       if (li > 0) {                                             // the previous store has finished reading the staging box
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-        __syncwarp();
       }
+      {   // this warp's 64 bias values as fp32 (lane l converts columns 2 l, 2 l + 1)
+        float2 b2 = make_float2(0.f, 0.f);
+        if (p.bias) b2 = load_pair_f32<T>(reinterpret_cast<const T*>(p.bias) + col0 + 2 * lane);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(gt_u32(bias_s) + lane * 8), "f"(b2.x), "f"(b2.y) : "memory");
+      }
+      __syncwarp();
 #pragma unroll 1
       for (int c = 0; c < EPI_COLS / 32; ++c) {
         uint32_t v[32];
@@ -270,34 +295,32 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           __syncwarp();
           if (lane == 0) gt_mbar_arrive(&acc_free[a]);
         }
-        const int col = col0 + c * 32;
         uint32_t o[16];
-        const T* bp = reinterpret_cast<const T*>(p.bias) + col;
+        const uint32_t b4 = gt_u32(bias_s + c * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float bf[8];
-          if (p.bias) load16_as_f32<T>(bp + j * 8, bf);
-          else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bf[e] = 0.f;
+        for (int j = 0; j < 8; ++j) {
+          float4 bb;                                // broadcast read: columns 4 j .. 4 j + 3 of the chunk
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(b4 + j * 16));
+          float x0, x1, x2, x3;
+          gt_unpk(gt_add2(gt_pk(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), gt_pk(bb.x, bb.y)), x0, x1);
+          gt_unpk(gt_add2(gt_pk(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), gt_pk(bb.z, bb.w)), x2, x3);
+          if (EPI == 1) {
+            gt_gelu2(x0, x1);
+            gt_gelu2(x2, x3);
           }
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float x0 = __uint_as_float(v[j * 8 + e]) + bf[e], x1 = __uint_as_float(v[j * 8 + e + 1]) + bf[e + 1];
-            if (EPI == 1) gt_gelu2(x0, x1);
-            o[j * 4 + e / 2] = gt_pack<T>(x0, x1);
-          }
+          o[2 * j] = gt_pack<T>(x0, x1);
+          o[2 * j + 1] = gt_pack<T>(x2, x3);
         }
         if (EPI == 2) {   // box c = one head: [32 rows x 64 B], SWIZZLE_64B (16-byte chunk ^ bits 1-2 of the row)
-          unsigned char* bx = stg + c * 2048 + lane * 64;
+          const uint32_t bx = gt_u32(stg) + c * 2048 + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(bx + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+            gt_sts128(bx + ((j ^ ((lane >> 1) & 3)) << 4), o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
         } else {          // one box [32 rows x 128 B], SWIZZLE_128B (16-byte chunk ^ row % 8)
-          unsigned char* bx = stg + lane * 128;
+          const uint32_t bx = gt_u32(stg) + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(bx + (((c * 4 + j) ^ (lane & 7)) << 4)) = make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+            gt_sts128(bx + (((c * 4 + j) ^ (lane & 7)) << 4), o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -396,6 +419,9 @@ extern "C" int psalm_linear_fused(const void* a, long long a_row_stride, const v
   p.bias = bias; p.out = out; p.M = (int)M; p.N = N; p.K = K; p.epilogue = epilogue; p.S = (int)(epilogue == 2 ? rows_per_image : 1);
   p.tiles_m = (int)((M + gt::BM - 1) / gt::BM);
   p.tiles_n = N / gt::BN;
+  p.tn_shift = -1;
+  for (int sft = 0; sft < 16; ++sft)
+    if ((1 << sft) == p.tiles_n) p.tn_shift = sft;
   CUtensorMap ma, mw, mo;
   const bool maps_ok =
       gt_make_map(&ma, a, M, K, a_row_stride, gt::BK, gt::BM, CU_TENSOR_MAP_SWIZZLE_128B, dtype) &&

@@ -30,6 +30,11 @@ def timeit(fn, flush, iters=20):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, help="run one shape by name")
+    ap.add_argument("--once", action="store_true", help="one fused call per shape (profiler runs)")
+    args = ap.parse_args()
     B = int(os.environ.get("B", "4"))
     dt = torch.bfloat16
     hbm = 6650.0
@@ -41,6 +46,8 @@ def main():
     shapes = [("swin_fc1_stage%d" % s, B * (256 >> s) ** 2, 512 << s, 128 << s, "gelu_erf", 0) for s in range(4)]
     shapes.append(("msda_value_proj", B * 21504, 256, 256, "head_major", 21504))
     for name, M, N, K, epi, S in shapes:
+        if args.only and name != args.only:
+            continue
         x = torch.randn(M, K, generator=g).to(dt).cuda()
         w = (torch.randn(N, K, generator=g) * K ** -0.5).to(dt).cuda()
         b = torch.randn(N, generator=g).to(dt).cuda()
@@ -49,6 +56,11 @@ def main():
         else:
             lib = lambda: F.linear(x, w, b).view(M // S, S, 8, 32).permute(0, 2, 1, 3).contiguous()
         ours = lambda: kernels.linear_fused(x, w, b, epi, S)
+        if args.once:
+            ours()
+            ours()
+            torch.cuda.synchronize()
+            continue
         t_lib, t_ours = timeit(lib, flush), timeit(ours, flush)
         nbytes = 2 * (M * K + N * K + M * N)
         print(f"{name:18s} M={M:7d} N={N:5d} K={K:5d}  library {t_lib:7.1f} us   fused {t_ours:7.1f} us   "
