@@ -278,6 +278,12 @@ int psalm_linear_fused_supported(long long M, int N, int K, int epilogue, long l
 int psalm_linear_fused(const void* a, long long a_row_stride, const void* w, const void* bias, void* out, long long M, int N,
                        int K, int epilogue, long long rows_per_image, int dtype, void* stream);
 
+/* PatchMerging's 2x2 gather + LayerNorm over the 4C concatenated channels (multimodal_encoder/swin_trans.py:269-296:
+ * F.pad to even H / W, x0..x3 strided slices, torch.cat, self.norm) in one pass: x [B,H,W,C] token-major ->
+ * y [B, ceil(H/2)*ceil(W/2), 4C] normalised, ready for the `reduction` Linear.  C in {128, 256, 512}. */
+int psalm_patch_merge_layernorm(const void* x, const void* weight, const void* bias, void* y, int B, int H, int W, int C,
+                                float eps, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

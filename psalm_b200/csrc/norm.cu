@@ -100,6 +100,74 @@ __global__ void __launch_bounds__(128) add_layernorm_kernel(const T* __restrict_
   }
 }
 
+// ---- PatchMerging gather + LayerNorm (swin_trans.py:269-296) -----------------------------------------
+// y[b, i, j, :] = LN(cat(x[b, 2i, 2j], x[b, 2i+1, 2j], x[b, 2i, 2j+1], x[b, 2i+1, 2j+1])) over 4C channels, pixels beyond
+// an odd H / W are zeros (F.pad before the slicing) and take part in the statistics.  Replaces the four strided slices +
+// torch.cat (a 4C-wide copy of the map) in front of the norm.  CPL = 4-element chunks per lane over the 4C row.
+template <typename T, int CPL>
+__global__ void __launch_bounds__(128) patch_merge_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                                    const T* __restrict__ b, T* __restrict__ y, int B, int H,
+                                                                    int W, float eps) {
+  constexpr int C4 = 128 * CPL, C = C4 / 4;
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const long long rows = (long long)B * H2 * W2;
+  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int j = (int)(row % W2), i = (int)((row / W2) % H2), bi = (int)(row / ((long long)W2 * H2));
+  float v[CPL][4];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int off = (c * 32 + lane) * 4;
+    const int q = off / C, cc = off - q * C;
+    const int yy = 2 * i + (q & 1), xx = 2 * j + (q >> 1);
+    if (yy < H && xx < W) load4<T>(x + (((size_t)bi * H + yy) * W + xx) * C + cc, v[c]);
+    else v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s += v[c][e];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / C4);
+  float qd = 0.f;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d = v[c][e] - mean;
+      qd = fmaf(d, d, qd);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qd += __shfl_xor_sync(0xffffffffu, qd, o);
+  const float rstd = rsqrtf(qd * (1.f / C4) + eps);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int off = (c * 32 + lane) * 4;
+    float g[4], bb[4], o4[4];
+    load4<T>(w + off, g);
+    load4<T>(b + off, bb);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o4[e] = (v[c][e] - mean) * rstd * g[e] + bb[e];
+    store4<T>(y + (size_t)row * C4 + off, o4);
+  }
+}
+
+template <typename T>
+static int launch_pm(const void* x, const void* w, const void* b, void* y, int B, int H, int W, int C, float eps, cudaStream_t st) {
+  const long long rows = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+#define PM(CPL) patch_merge_layernorm_kernel<T, CPL><<<grid, 128, 0, st>>>((const T*)x, (const T*)w, (const T*)b, (T*)y, B, H, W, eps)
+  switch (C) {
+    case 128: PM(4); break;
+    case 256: PM(8); break;
+    case 512: PM(16); break;
+    default: set_error("patch_merge_layernorm: C=%d unsupported (128/256/512)", C); return PSALM_E_UNSUPPORTED;
+  }
+#undef PM
+  return check_launch("patch_merge_layernorm_kernel");
+}
+
 // ---- GroupNorm on token-major maps -----------------------------------------------------------------
 // Deterministic (no atomics): (1) per-CTA partial (sum, sumsq) per group over a slice of 256 tokens,
 // reduced inside the CTA in a fixed order; (2) a finalize kernel adds the partials of each (batch, group)
@@ -261,5 +329,19 @@ extern "C" int psalm_groupnorm_tokens(const void* x, const void* pre_bias, const
     case PSALM_BF16: return launch_gn<__nv_bfloat16>(x, pre_bias, weight, bias, y, stats_workspace, B, N, C, groups, eps, relu, st);
   }
   set_error("groupnorm_tokens: unknown dtype %d", dtype);
+  return PSALM_E_ARG;
+}
+
+extern "C" int psalm_patch_merge_layernorm(const void* x, const void* weight, const void* bias, void* y, int B, int H, int W,
+                                           int C, float eps, int dtype, void* stream) {
+  PSALM_REQUIRE(x && weight && bias && y, "patch_merge_layernorm: null pointer");
+  PSALM_REQUIRE(B > 0 && H > 0 && W > 0, "patch_merge_layernorm: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case PSALM_F32: return launch_pm<float>(x, weight, bias, y, B, H, W, C, eps, st);
+    case PSALM_F16: return launch_pm<__half>(x, weight, bias, y, B, H, W, C, eps, st);
+    case PSALM_BF16: return launch_pm<__nv_bfloat16>(x, weight, bias, y, B, H, W, C, eps, st);
+  }
+  set_error("patch_merge_layernorm: unknown dtype %d", dtype);
   return PSALM_E_ARG;
 }

@@ -315,6 +315,23 @@ def linear_act(x, weight, bias, act):
     return F.relu(y) if act == "relu" else F.gelu(y, approximate="tanh")
 
 
+@_on_device
+def patch_merge_layer_norm(x, H, W, weight, bias, eps=1e-5):
+    """Swin PatchMerging gather + LayerNorm (swin_trans.py:269-296): x [B, H*W, C] -> [B, ceil(H/2)*ceil(W/2), 4C]
+    normalised over the concatenated 2x2 neighbourhood (zero padded to even H / W)."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias")):
+        _chk(t, "patch_merge_layer_norm." + n)
+    B, N, C = x.shape
+    if N != H * W or weight.numel() != 4 * C:
+        raise _lib.PsalmKernelError("patch_merge_layer_norm: x is [B, H*W, C], weight / bias have 4C entries")
+    y = torch.empty((B, ((H + 1) // 2) * ((W + 1) // 2), 4 * C), dtype=x.dtype, device=x.device)
+    rc = _lib.lib().psalm_patch_merge_layernorm(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), B, H, W, C,
+                                                float(eps), _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
+    _lib.check(rc, "psalm_patch_merge_layernorm")
+    _count()
+    return y
+
+
 LINEAR_FUSED = True   # False: library GEMM + separate elementwise pass (A/B runs)
 _EPILOGUES = {"bias": 0, "gelu_erf": 1, "head_major": 2}
 

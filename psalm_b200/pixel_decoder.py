@@ -151,8 +151,12 @@ class MSDeformAttnPixelDecoder:
         H2, W2 = sizes[0]
         cur = kernels.group_norm_tokens(F.linear(toks[0], w["ad.w"], w["ad.b"]), w["ad.gw"], w["ad.gb"], relu=True)
         Hl, Wl = shapes[-1]
-        up = kernels.bilinear_tokens(outs[-1], Hl, Wl, H2, W2)   # fp32 math, rounded to dtype like `.to(x.dtype)`
-        y = (cur + up).view(B, H2, W2, cfg.hidden).permute(0, 3, 1, 2)   # channels-last NCHW view
+        if self.dtype == torch.float32:
+            up = kernels.bilinear_tokens(outs[-1], Hl, Wl, H2, W2)   # fp32 math, rounded to dtype like `.to(x.dtype)`
+            y = cur + up
+        else:   # 16-bit storage: the up-sampled map is added in the resampling kernel (one pass instead of three)
+            y = kernels.bilinear_tokens(outs[-1], Hl, Wl, H2, W2, out=cur, accumulate=True)
+        y = y.view(B, H2, W2, cfg.hidden).permute(0, 3, 1, 2)   # channels-last NCHW view
         # the conv runs without its bias (a separate broadcast-add pass in cuDNN); GroupNorm adds it in-kernel
         y = F.conv2d(y, w["l1.w"], None, padding=1).permute(0, 2, 3, 1).reshape(B, H2 * W2, cfg.hidden)
         y = kernels.group_norm_tokens(y.contiguous(), w["l1.gw"], w["l1.gb"], relu=True, pre_bias=w["l1.b"])

@@ -122,13 +122,9 @@ class SwinTransformer:
             sizes.append((Wh, Ww))
             if s < len(cfg.depths) - 1:  # PatchMerging swin_trans.py:269-296
                 p = "layers.%d.downsample." % s
-                xm = x.view(B, Wh, Ww, C)
-                if Wh % 2 == 1 or Ww % 2 == 1:
-                    xm = F.pad(xm, (0, 0, 0, Ww % 2, 0, Wh % 2))
-                xm = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1)
+                # pad to even size + the four strided slices + cat + norm: one gather-LayerNorm kernel
+                xm = kernels.patch_merge_layer_norm(x.contiguous(), Wh, Ww, w[p + "norm.w"], w[p + "norm.b"])
                 Wh, Ww = (Wh + 1) // 2, (Ww + 1) // 2
-                xm = xm.reshape(B, Wh * Ww, 4 * C)
-                xm = LN(xm.contiguous(), w[p + "norm.w"], w[p + "norm.b"])
                 x = F.linear(xm, w[p + "red.w"])
                 C = 2 * C
         return outs, sizes

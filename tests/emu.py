@@ -176,7 +176,7 @@ def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
                  "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify", "masked_cross_attention", "kv_cache_write",
-                 "paged_decode_attention", "linear_fused_supported"):
+                 "paged_decode_attention", "linear_fused_supported", "patch_merge_layer_norm"):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 
@@ -219,3 +219,13 @@ def postproc_fused(logits, H, W, probsT=None, wq=None, negq=None, slot_query=Non
 
 def linear_fused_supported(*a, **k):
     return False
+
+
+def patch_merge_layer_norm(x, H, W, weight, bias, eps=1e-5):
+    B, N, C = x.shape
+    xm = x.view(B, H, W, C)
+    if H % 2 == 1 or W % 2 == 1:
+        xm = F.pad(xm, (0, 0, 0, W % 2, 0, H % 2))
+    xm = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1)
+    xm = xm.reshape(B, -1, 4 * C)
+    return add_layer_norm(xm.contiguous(), weight, bias, eps)

@@ -57,3 +57,39 @@ def test_unsupported_width_raises():
     x = torch.zeros(4, 96, device="cuda")
     with pytest.raises(PsalmKernelError):
         kernels.add_layer_norm(x, torch.ones(96, device="cuda"), torch.zeros(96, device="cuda"))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("H,W,C", [(16, 24, 128), (15, 9, 256), (7, 8, 512), (1, 5, 128)])
+def test_patch_merge_layernorm(dt, H, W, C):
+    """Swin PatchMerging gather + LayerNorm in one kernel vs pad + strided slices + cat + LayerNorm
+    (swin_trans.py:280-293), including odd H / W (zero padding takes part in the statistics)."""
+    torch.manual_seed(H * 100 + W + C)
+    x = (torch.randn(3, H * W, C) * 1.5 + 0.3).to(DT[dt])
+    w = (1 + 0.1 * torch.randn(4 * C)).to(DT[dt])
+    b = (0.1 * torch.randn(4 * C)).to(DT[dt])
+    ref = emu.patch_merge_layer_norm(x, H, W, w, b)
+    y = kernels.patch_merge_layer_norm(x.cuda(), H, W, w.cuda(), b.cuda())
+    assert y.shape == ref.shape
+    _close(y, ref, dt)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
+def test_bilinear_tokens_vector_kernel_equals_scalar_kernel(dt):
+    """The 16-byte-vector resampling kernel evaluates the scalar kernel's expression (reached through an fp32-output
+    call): equal up to the 16-bit rounding of the output."""
+    torch.manual_seed(5)
+    x = torch.randn(2, 24 * 20, 64).to(DT[dt]).cuda()
+    for Ho, Wo in ((12, 10), (6, 5), (48, 40), (17, 13)):
+        vec = kernels.bilinear_tokens(x, 24, 20, Ho, Wo)
+        if dt == "f32":
+            ref = emu.bilinear_tokens(x.cpu(), 24, 20, Ho, Wo)
+            assert (vec.cpu() - ref).abs().max() < 1e-5
+        else:
+            scalar = kernels.bilinear_tokens(x, 24, 20, Ho, Wo, out_dtype=torch.float32)     # fp32 result of the scalar kernel
+            ulp = 2.0 ** (-10 if dt == "f16" else -7)                                         # FMA contraction may differ: 1 ulp
+            assert bool(((vec.float() - scalar).abs() <= ulp * scalar.abs() + 1e-6).all())
+        acc0 = torch.randn(2, Ho * Wo, 64).to(DT[dt]).cuda()
+        acc = kernels.bilinear_tokens(x, 24, 20, Ho, Wo, out=acc0.clone(), accumulate=True)
+        ref = emu.bilinear_tokens(x.cpu(), 24, 20, Ho, Wo, out=acc0.cpu().clone(), accumulate=True)
+        assert (acc.float().cpu() - ref.float()).abs().max() <= (2e-5 if dt == "f32" else 4e-2)
