@@ -468,8 +468,104 @@ __global__ void flash_combine_kernel(Policy pol, AttnDims dm, const float* __res
 // ------------------------------------------------------------------------------------------------
 // Swin window kernel: grid = (B*nW, nh), block = 288 (9 warps), N = 144 tokens, head_dim 32
 // ------------------------------------------------------------------------------------------------
+// keys [16 NP0, 16 NP1) of one window for the 16 query rows of a warp: S = Q K^T, + bias (+ shift mask), running max /
+// sum update, O = O * alpha + P V.  LD = 40 (32 + 8 padding), scores in the log2 domain.
+template <typename T, int NP0, int NP1>
+__device__ __forceinline__ void win_keys(const T* __restrict__ Ks, const T* __restrict__ Vs, const uint32_t (&qa)[2][4],
+                                         const float* __restrict__ rc0, const float* __restrict__ rc1,
+                                         const short* __restrict__ coff, const unsigned char* __restrict__ reg, int reg0,
+                                         int reg1, bool wmask, float scl, int lane, int t4, float (&o)[4][4],
+                                         float (&mrun)[2], float (&sum)[2]) {
+  constexpr int LD = 40, NT = 2 * (NP1 - NP0);
+  float s[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+    for (int np = NP0; np < NP1; ++np) {
+      uint32_t kb[4];
+      const int mi = lane >> 3;
+      ldsm_x4(kb, &Ks[(np * 16 + (lane & 7) + (mi >> 1) * 8) * LD + ks * 16 + (mi & 1) * 8]);
+      mma16816<T>(s[2 * (np - NP0)], qa[ks], kb[0], kb[1]);
+      mma16816<T>(s[2 * (np - NP0) + 1], qa[ks], kb[2], kb[3]);
+    }
+  }
+  float mx[2] = {mrun[0], mrun[1]};
+  if (!wmask) {                    // window does not touch the wrapped border: no shift mask (warp-uniform)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int kj = (2 * NP0 + nt) * 8 + 2 * t4;
+      const int c2 = *reinterpret_cast<const int*>(&coff[kj]);   // column offsets of keys kj, kj + 1
+      const int ca = (short)(c2 & 0xffff), cb = c2 >> 16;
+      s[nt][0] = fmaf(s[nt][0], scl, rc0[ca]);
+      s[nt][1] = fmaf(s[nt][1], scl, rc0[cb]);
+      s[nt][2] = fmaf(s[nt][2], scl, rc1[ca]);
+      s[nt][3] = fmaf(s[nt][3], scl, rc1[cb]);
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+  } else {
+    constexpr float kNeg = -100.f * kLog2e;   // the reference's additive -100 (swin_trans.py:232-240)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int kj = (2 * NP0 + nt) * 8 + 2 * t4;
+      const int c2 = *reinterpret_cast<const int*>(&coff[kj]);
+      const int ca = (short)(c2 & 0xffff), cb = c2 >> 16;
+      const int ra = reg[kj], rb = reg[kj + 1];
+      s[nt][0] = fmaf(s[nt][0], scl, rc0[ca]) + (ra != reg0 ? kNeg : 0.f);
+      s[nt][1] = fmaf(s[nt][1], scl, rc0[cb]) + (rb != reg0 ? kNeg : 0.f);
+      s[nt][2] = fmaf(s[nt][2], scl, rc1[ca]) + (ra != reg1 ? kNeg : 0.f);
+      s[nt][3] = fmaf(s[nt][3], scl, rc1[cb]) + (rb != reg1 ? kNeg : 0.f);
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  if (NP0 > 0) {   // scores are finite (bias and the -100 mask are finite), so mx is finite from the first call on
+    const float a0 = fast_exp2(mrun[0] - mx[0]), a1 = fast_exp2(mrun[1] - mx[1]);
+    sum[0] *= a0;
+    sum[1] *= a1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[i][0] *= a0; o[i][1] *= a0;
+      o[i][2] *= a1; o[i][3] *= a1;
+    }
+  }
+  mrun[0] = mx[0];
+  mrun[1] = mx[1];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = fast_exp2(s[nt][0] - mx[0]); s[nt][1] = fast_exp2(s[nt][1] - mx[0]);
+    s[nt][2] = fast_exp2(s[nt][2] - mx[1]); s[nt][3] = fast_exp2(s[nt][3] - mx[1]);
+    sum[0] += s[nt][0] + s[nt][1];
+    sum[1] += s[nt][2] + s[nt][3];
+  }
+#pragma unroll
+  for (int kk = NP0; kk < NP1; ++kk) {
+    const int k2 = 2 * (kk - NP0);
+    uint32_t pa[4];
+    pa[0] = pack2<T>(s[k2][0], s[k2][1]);
+    pa[1] = pack2<T>(s[k2][2], s[k2][3]);
+    pa[2] = pack2<T>(s[k2 + 1][0], s[k2 + 1][1]);
+    pa[3] = pack2<T>(s[k2 + 1][2], s[k2 + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      uint32_t vb[4];
+      const int mi = lane >> 3;
+      ldsm_x4_t(vb, &Vs[(kk * 16 + (lane & 7) + (mi & 1) * 8) * LD + dp * 16 + (mi >> 1) * 8]);
+      mma16816<T>(o[2 * dp], pa, vb[0], vb[1]);
+      mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
+    }
+  }
+}
+
 template <typename T, int HPC>
-__global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict__ qkv, const T* __restrict__ qkv_bias,
+__global__ void __launch_bounds__(288, 3) window_mma_kernel(const T* __restrict__ qkv, const T* __restrict__ qkv_bias,
                                                             const float* __restrict__ rel, T* __restrict__ out,
                                                             int H, int W, int Hp, int Wp, int shift, int nh, int C,
                                                             int nWx, int nW) {
@@ -552,89 +648,22 @@ __global__ void __launch_bounds__(288, 2) window_mma_kernel(const T* __restrict_
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
       ldsm_x4(qa[ks], &Qs[(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8]);
-    float s[18][4];
-#pragma unroll
-    for (int i = 0; i < 18; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-      for (int np = 0; np < 9; ++np) {
-        uint32_t kb[4];
-        const int mi = lane >> 3;
-        ldsm_x4(kb, &Ks[(np * 16 + (lane & 7) + (mi >> 1) * 8) * LD + ks * 16 + (mi & 1) * 8]);
-        mma16816<T>(s[2 * np], qa[ks], kb[0], kb[1]);
-        mma16816<T>(s[2 * np + 1], qa[ks], kb[2], kb[3]);
-      }
-    }
+    // The 144 keys are processed as 80 + 64 with a running (max, sum) and one rescale of the output accumulators:
+    // 40 score registers per thread instead of 72, which brings the kernel from 96 to <= 72 registers = 3 CTAs per SM
+    // (27 warps instead of 18; the kernel is latency bound, profiles/r1m_window_mma_stage2_ncu_details.txt).
     const float* rc0 = relc + stage * (NREL + 3) + rb0;
     const float* rc1 = relc + stage * (NREL + 3) + rb1;
-    float mx[2] = {-INFINITY, -INFINITY};
     const float scl = sc * kLog2e;   // scores go straight to the log2 domain: s * scale * log2e + bias * log2e
-    if (!wmask) {                    // window does not touch the wrapped border: no shift mask (warp-uniform)
+    float o[4][4];
 #pragma unroll
-      for (int nt = 0; nt < 18; ++nt) {
-        const int kj = nt * 8 + 2 * t4;
-        const int c2 = *reinterpret_cast<const int*>(&coff[kj]);   // column offsets of keys kj, kj + 1
-        const int ca = (short)(c2 & 0xffff), cb = c2 >> 16;
-        s[nt][0] = fmaf(s[nt][0], scl, rc0[ca]);
-        s[nt][1] = fmaf(s[nt][1], scl, rc0[cb]);
-        s[nt][2] = fmaf(s[nt][2], scl, rc1[ca]);
-        s[nt][3] = fmaf(s[nt][3], scl, rc1[cb]);
-        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-      }
-    } else {
-      constexpr float kNeg = -100.f * kLog2e;   // the reference's additive -100 (swin_trans.py:232-240)
-#pragma unroll
-      for (int nt = 0; nt < 18; ++nt) {
-        const int kj = nt * 8 + 2 * t4;
-        const int c2 = *reinterpret_cast<const int*>(&coff[kj]);
-        const int ca = (short)(c2 & 0xffff), cb = c2 >> 16;
-        const int ra = reg[kj], rb = reg[kj + 1];
-        s[nt][0] = fmaf(s[nt][0], scl, rc0[ca]) + (ra != reg0 ? kNeg : 0.f);
-        s[nt][1] = fmaf(s[nt][1], scl, rc0[cb]) + (rb != reg0 ? kNeg : 0.f);
-        s[nt][2] = fmaf(s[nt][2], scl, rc1[ca]) + (ra != reg1 ? kNeg : 0.f);
-        s[nt][3] = fmaf(s[nt][3], scl, rc1[cb]) + (rb != reg1 ? kNeg : 0.f);
-        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-      }
-    }
-    float sum[2] = {0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-    }
-#pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-      s[nt][0] = fast_exp2(s[nt][0] - mx[0]); s[nt][1] = fast_exp2(s[nt][1] - mx[0]);
-      s[nt][2] = fast_exp2(s[nt][2] - mx[1]); s[nt][3] = fast_exp2(s[nt][3] - mx[1]);
-      sum[0] += s[nt][0] + s[nt][1];
-      sum[1] += s[nt][2] + s[nt][3];
-    }
+    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float mrun[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
+    win_keys<T, 0, 5>(Ks, Vs, qa, rc0, rc1, coff, reg, reg0, reg1, wmask, scl, lane, t4, o, mrun, sum);
+    win_keys<T, 5, 9>(Ks, Vs, qa, rc0, rc1, coff, reg, reg0, reg1, wmask, scl, lane, t4, o, mrun, sum);
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
       sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
-    }
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 9; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack2<T>(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack2<T>(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack2<T>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack2<T>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-      for (int dp = 0; dp < 2; ++dp) {
-        uint32_t vb[4];
-        const int mi = lane >> 3;
-        ldsm_x4_t(vb, &Vs[(kk * 16 + (lane & 7) + (mi & 1) * 8) * LD + dp * 16 + (mi >> 1) * 8]);
-        mma16816<T>(o[2 * dp], pa, vb[0], vb[1]);
-        mma16816<T>(o[2 * dp + 1], pa, vb[2], vb[3]);
-      }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -789,7 +818,7 @@ static int launch_window(const void* qkv, const void* qkv_bias, const float* rel
     window_mma_kernel<T, HPC><<<grid, 288, smem, st>>>((const T*)qkv, (const T*)qkv_bias, rel, (T*)out, H, W, Hp,   \
                                                       Wp, shift, nh, C, nWx, nW);                                 \
   } while (0)
-  // enough CTAs for >= 2 waves of 148 SMs x 2 CTAs, otherwise prefer deeper per-CTA pipelining
+  // enough CTAs for >= 2 waves of 148 SMs x 3 CTAs, otherwise prefer deeper per-CTA pipelining
   const long long windows = (long long)B * nW;
   if (nh % 4 == 0 && windows * (nh / 4) >= 600) WIN(4);
   else if (nh % 2 == 0 && windows * (nh / 2) >= 148) WIN(2);
