@@ -284,6 +284,14 @@ int psalm_linear_fused(const void* a, long long a_row_stride, const void* w, con
 int psalm_patch_merge_layernorm(const void* x, const void* weight, const void* bias, void* y, int B, int H, int W, int C,
                                 float eps, int dtype, void* stream);
 
+/* Region prompts: features of R regions = mean over P points of the bilinear samples
+ * (F.grid_sample, align_corners=True, zero padding) of the projector's token map.
+ * Replaces `region_pooling.forward` (visual_prompt_module/context_cluster.py:333-400, point_sample :43-68).
+ *   tokens [B, h*w, C] token-major (dtype), points [R, P, 2] fp32 = (y, x) in [0, 1] (mask pixel / mask size, as
+ *   context_cluster.py:349-352 builds them), region_image [R] int32 = image of every region, out [R, C] (dtype). */
+int psalm_region_pool(const void* tokens, const float* points, const int* region_image, void* out, int B, int h, int w,
+                      int C, int R, int P, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

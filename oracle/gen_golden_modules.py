@@ -90,9 +90,13 @@ def run_case(task, H, W, n_classes, seed, batch=1, ragged=False):
               "refer_embedding_indices", "is_thing_list"):
         if k in inp:
             kw[k] = inp[k]
+    if task == "region":
+        torch.manual_seed(1234)   # region_pooling draws its sample points from the global CPU generator
     ref_results = m.eval_seg(**kw)
     for h in hs:
         h.remove()
+    if task == "region":
+        torch.manual_seed(1234)   # the oracle makes the same draws in the same order
 
     # ---- oracle on the same data ----
     ores, oi = O.eval_seg(sd, inp["input_ids"], inp["attention_mask"], inp["images"], inp["seg_info"],
@@ -133,6 +137,11 @@ def run_case(task, H, W, n_classes, seed, batch=1, ragged=False):
     if pr["pred_SEG_logits"] is not None:
         rep["SEG"] = rel(oi["predictor"]["pred_SEG_logits"], pr["pred_SEG_logits"])
         gold["pred_SEG_logits"] = pr["pred_SEG_logits"].numpy()
+    if pr.get("pred_region_logits") is not None:
+        for b, (a, r_) in enumerate(zip(oi["predictor"]["pred_region_logits"], pr["pred_region_logits"])):
+            rep["region_logits_%d" % b] = rel(a, r_)
+            gold["pred_region_logits_%d" % b] = r_.numpy()
+            gold["region_points_%d" % b] = oi["region_points"][b].numpy()
     # ---- post-processed results (image 0 only: the reference returns inside the loop, LP:1472) ----
     r0, o0 = ref_results[0], ores[0]
     if "sem_seg" in r0:
@@ -145,7 +154,15 @@ def run_case(task, H, W, n_classes, seed, batch=1, ragged=False):
         gold["panoptic_info"] = np.array([[d["id"], int(d["isthing"]), d["category_id"]] for d in info], dtype=np.int64).reshape(-1, 3)
         opan, oinfo = o0["panoptic_seg"]
         rep["panoptic_equal"] = (bool(torch.equal(opan, pan)), oinfo == info)
-    if "instances" in r0:
+    if task == "region":
+        inst = r0["instances"]
+        gold["region_scores"] = inst.scores.numpy()
+        gold["region_mask_area"] = inst.pred_masks.flatten(1).sum(1).numpy()
+        gold["region_gt_idx"], gold["region_gt"] = subsample(r0["gt"], n=8192)
+        rep["region_scores"] = rel(o0["instances"]["scores"], inst.scores)
+        rep["region_masks_equal"] = bool(torch.equal(o0["instances"]["pred_masks"], inst.pred_masks))
+        rep["region_gt"] = rel(o0["gt"], r0["gt"])
+    elif "instances" in r0:
         inst = r0["instances"]
         sc = inst.scores
         order = torch.argsort(sc, descending=True, stable=True)
@@ -168,12 +185,19 @@ CASES = [
     ("panoptic", 200, 264, 12, 3, 1, False),     # ragged: window padding, odd patch-merge sizes, 32-padding crop
     ("referring", 192, 192, 0, 5, 1, False),
     ("panoptic", 96, 128, 7, 7, 2, True),        # batch 2, ragged prompts -> right padding + attention mask
+    ("region", 192, 192, 0, 9, 1, False),        # <region> prompts: point-sampled region features + REGION_proj head
 ]
 
 
 def main():
     reps = {}
+    only = sys.argv[1] if len(sys.argv) > 1 else None      # e.g. `python oracle/gen_golden_modules.py region`
+    rp = os.path.join(GOLD, "oracle_vs_reference_report.json")
+    if only and os.path.exists(rp):
+        reps = json.load(open(rp))
     for c in CASES:
+        if only and c[0] != only:
+            continue
         reps["%s_%dx%d_b%d" % (c[0], c[1], c[2], c[5])] = run_case(*c)
     with open(os.path.join(GOLD, "oracle_vs_reference_report.json"), "w") as f:
         json.dump(reps, f, indent=1)

@@ -223,12 +223,47 @@ def projector_forward(sd, pre, res5):
 
 
 # ------------------------------------------------------------------------------------------------
+# Region prompts — visual_prompt_module/context_cluster.py:31-40 (rand_sample_repeat), :43-68 (point_sample),
+# :333-400 (region_pooling); called from LP:791-797
+# ------------------------------------------------------------------------------------------------
+def sample_region_points(region_masks, num_sample_point=256):
+    """region_masks [K,H,W] (bool / 0-1) -> [K, num_sample_point, 2] normalised (y / H, x / W) positions of mask
+    pixels.  Draws from the GLOBAL CPU generator with the reference's calls in the reference's order (torch.randint
+    when a mask has fewer pixels than points, torch.randperm when it has more, context_cluster.py:31-40), so the
+    same torch.manual_seed gives the same points as the reference."""
+    wh = torch.tensor([region_masks[0].shape[0], region_masks[0].shape[1]])[None]
+    out = []
+    for m in region_masks:
+        x = m.nonzero() / wh
+        if x.shape[0] < num_sample_point:
+            idx = torch.randint(0, x.shape[0], (num_sample_point - x.shape[0],))
+            x = torch.cat((x, x[idx]), dim=0)
+        elif x.shape[0] > num_sample_point:
+            x = x[torch.randperm(x.shape[0])[:num_sample_point], :]
+        out.append(x)
+    return torch.stack(out)
+
+
+def region_pool(img_tok_b, points):
+    """img_tok_b [n_img, C] (projector output of one image, h = w = sqrt(n_img)); points [K,P,2] (y, x) in [0,1]
+    -> [K, 1, C]: grid_sample(align_corners=True) at the points, mean over P (context_cluster.py:355-371, :392)."""
+    h = w = int(math.sqrt(img_tok_b.shape[0]))
+    c = img_tok_b.shape[-1]
+    fmap = img_tok_b.reshape(h, w, c).permute(2, 0, 1).unsqueeze(0).repeat(points.shape[0], 1, 1, 1)
+    grid = (2.0 * points.flip(dims=(2,)).to(img_tok_b.dtype) - 1.0).unsqueeze(2)
+    fea = F.grid_sample(fmap.float(), grid.float(), align_corners=True).squeeze(3).to(img_tok_b.dtype)   # [K,C,P]
+    return fea.mean(-1).unsqueeze(1)
+
+
+# ------------------------------------------------------------------------------------------------
 # Sequence assembly — LP:767-971 / LP:581-766 (batch of B samples, ragged -> right padded)
 # ------------------------------------------------------------------------------------------------
 def assemble_sequence(sd, input_ids, attention_mask, image_features, class_name_ids=None, cls_indices=None,
-                      class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None):
+                      class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None,
+                      region_features=None):
     """Returns dict(inputs_embeds [B,T,C], attention_mask [B,T] bool, seg_query_mask [B,T],
-    class_name_embedding_indices [B,T] or None, refer_embedding_indices [B,T] or None)."""
+    class_name_embedding_indices [B,T] or None, refer_embedding_indices [B,T] or None, region_embedding_masks [B,T] or
+    None).  region_features: per sample [K,1,C] (LP:795-797), one per <region> token in order (LP:685-703)."""
     emb = sd["model.embed_tokens.weight"]
     seg_query = sd["seg_query"]
     B = input_ids.shape[0]
@@ -243,8 +278,11 @@ def assemble_sequence(sd, input_ids, attention_mask, image_features, class_name_
             uniq = uniq[uniq >= 0]
             cls_embeds = [emb[class_name_ids[b][ci == u]] for u in uniq]
         refer_embed = emb[token_refer_id[b]] if token_refer_id is not None else None  # LP:576-580
-        embeds, qmask, cidx, ridx = [], [], [], []
+        embeds, qmask, cidx, ridx, gmask = [], [], [], [], []
         cls_i = 0
+        region_i = 0
+        if region_features is not None:
+            assert (ids == REGION_TOKEN_INDEX).sum() == len(region_features[b])  # LP:592-594
         assert (ids == IMAGE_TOKEN_INDEX).sum() == 1 and (ids == SEG_TOKEN_INDEX).sum() == 1  # LP:588-589
         if cls_embeds is not None:
             assert (ids == CLS_TOKEN_INDEX).sum() == len(cls_embeds)  # LP:590-591
@@ -263,6 +301,7 @@ def assemble_sequence(sd, input_ids, attention_mask, image_features, class_name_
                             else torch.zeros(k, dtype=torch.long))
                 ridx.append(refer_embedding_indices[b][i:j] if refer_embedding_indices is not None
                             else torch.zeros(k, dtype=torch.long))
+                gmask.append(torch.zeros(k))
                 i = j
                 continue
             if t == IMAGE_TOKEN_INDEX:
@@ -275,17 +314,21 @@ def assemble_sequence(sd, input_ids, attention_mask, image_features, class_name_
                 qm, cv, rv = 0, cls_i, 0  # index value = running 1-based class counter (LP:671-673)
             elif t == REFER_TOKEN_INDEX:
                 e, qm, cv, rv = refer_embed, 0, 0, 1
+            elif t == REGION_TOKEN_INDEX:   # LP:684-703
+                e, qm, cv, rv = region_features[b][region_i], 0, 0, 0
+                region_i += 1
             else:
-                raise NotImplementedError("region tokens are out of scope (SURVEY.md §2 #8)")
+                raise ValueError("unknown sentinel id %d" % t)
             if e.dim() == 1:
                 e = e.unsqueeze(0)
             k = e.shape[0]
+            gmask.append(torch.full((k,), 1.0 if t == REGION_TOKEN_INDEX else 0.0))
             embeds.append(e)
             qmask.append(torch.full((k,), float(qm)))
             cidx.append(torch.full((k,), cv, dtype=torch.long))
             ridx.append(torch.full((k,), rv, dtype=torch.long))
             i += 1
-        per.append((torch.cat(embeds, 0), torch.cat(qmask, 0), torch.cat(cidx, 0), torch.cat(ridx, 0)))
+        per.append((torch.cat(embeds, 0), torch.cat(qmask, 0), torch.cat(cidx, 0), torch.cat(ridx, 0), torch.cat(gmask, 0)))
     T = max(p[0].shape[0] for p in per)
     C = per[0][0].shape[1]
     out_e = torch.zeros(B, T, C, dtype=per[0][0].dtype)
@@ -293,16 +336,18 @@ def assemble_sequence(sd, input_ids, attention_mask, image_features, class_name_
     out_c = torch.zeros(B, T, dtype=torch.long)
     out_r = torch.zeros(B, T, dtype=torch.long)
     out_m = torch.zeros(B, T, dtype=torch.bool)
-    for b, (e, qm, cv, rv) in enumerate(per):
+    out_g = torch.zeros(B, T)
+    for b, (e, qm, cv, rv, gm) in enumerate(per):
         t = e.shape[0]
-        out_e[b, :t], out_q[b, :t], out_c[b, :t], out_r[b, :t] = e, qm, cv, rv
+        out_e[b, :t], out_q[b, :t], out_c[b, :t], out_r[b, :t], out_g[b, :t] = e, qm, cv, rv, gm
         # LP:935-949 / 964-969: new tokens are attendable, then the caller's mask, then right padding False
         left = t - input_ids.shape[1]
         out_m[b, :left] = True
         out_m[b, left:t] = attention_mask[b].bool()
     return dict(inputs_embeds=out_e, attention_mask=out_m, seg_query_mask=out_q,
                 class_name_embedding_indices=out_c if class_name_embedding_indices is not None else None,
-                refer_embedding_indices=out_r if refer_embedding_indices is not None else None)
+                refer_embedding_indices=out_r if refer_embedding_indices is not None else None,
+                region_embedding_masks=out_g if region_features is not None else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -450,8 +495,12 @@ def _mlp(sd, pre, x, n):  # DEC:187-199
     return x
 
 
-def prediction_heads(sd, pre, output, mask_features, target_size, SEG_embedding, class_name_embedding, nh=8):
+def prediction_heads(sd, pre, output, mask_features, target_size, SEG_embedding, class_name_embedding, nh=8,
+                     region_embedding_list=None, region_out=None):
     dec = _ln(sd, pre + "decoder_norm", output).transpose(0, 1)
+    if region_embedding_list is not None and region_out is not None:   # DEC:737-745 (seg_proj is on)
+        dr = _mlp(sd, pre + "REGION_proj.", dec, 2)
+        region_out.append([torch.einsum("kd,ld->kl", re, d) for d, re in zip(dr, region_embedding_list)])
     SEG_class = None
     if SEG_embedding is not None:
         SEG_class = torch.einsum("bld,bcd->blc", _mlp(sd, pre + "SEG_proj.", dec, 2), SEG_embedding)
@@ -466,7 +515,7 @@ def prediction_heads(sd, pre, output, mask_features, target_size, SEG_embedding,
 
 
 def predictor_forward(sd, pre, ms_feats, mask_features, seg_query, SEG_embedding=None, class_name_embedding=None,
-                      nh=8, return_all=False):
+                      nh=8, return_all=False, region_embedding_list=None):
     src, pos, sizes = [], [], []
     for i in range(3):  # DEC:607-614  (input_proj is identity: in_channels == hidden_dim, DEC:475-479)
         x = ms_feats[i]
@@ -476,8 +525,9 @@ def predictor_forward(sd, pre, ms_feats, mask_features, seg_query, SEG_embedding
     bs = src[0].shape[1]
     query_embed = sd[pre + "query_embed.weight"].unsqueeze(1).repeat(1, bs, 1)  # DEC:619
     output = seg_query.permute(1, 0, 2)
+    region_trace = []
     SEGc, clsc, omask, attn_mask = prediction_heads(sd, pre, output, mask_features, sizes[0], SEG_embedding,
-                                                    class_name_embedding, nh)
+                                                    class_name_embedding, nh, region_embedding_list, region_trace)
     trace = [(SEGc, clsc, omask, attn_mask)]
     layer_outputs = [output]        # decoder state before layer 0, then after every layer ([Q, B, C])
     n_layers = 0
@@ -498,10 +548,12 @@ def predictor_forward(sd, pre, ms_feats, mask_features, seg_query, SEG_embedding
         t2 = _lin(sd, p + "linear2", F.relu(_lin(sd, p + "linear1", output)))
         output = _ln(sd, p + "norm", output + t2)
         SEGc, clsc, omask, attn_mask = prediction_heads(sd, pre, output, mask_features, sizes[(i + 1) % 3],
-                                                        SEG_embedding, class_name_embedding, nh)
+                                                        SEG_embedding, class_name_embedding, nh, region_embedding_list,
+                                                        region_trace)
         trace.append((SEGc, clsc, omask, attn_mask))
         layer_outputs.append(output)
-    out = dict(pred_SEG_logits=SEGc, pred_class_name_logits=clsc, pred_masks=omask)
+    out = dict(pred_SEG_logits=SEGc, pred_class_name_logits=clsc, pred_masks=omask,
+               pred_region_logits=region_trace[-1] if region_trace else None)
     if return_all:
         out["trace"] = trace
         out["layer_outputs"] = layer_outputs
@@ -565,6 +617,13 @@ def seg_instance_inference(SEG_cls, mask_pred, topk):  # LP:308-324
     return dict(pred_masks=pm, scores=s * ms, query_index=idx)
 
 
+def region_inference(region_cls, mask_pred):  # LP:387-400
+    pm = (mask_pred > 0).float()
+    mask_scores = (mask_pred.sigmoid().flatten(1) * pm.flatten(1)).sum(1) / (pm.flatten(1).sum(1) + 1e-6)
+    scores = (region_cls.sigmoid() * mask_scores[None, ...].repeat(region_cls.shape[0], 1)).transpose(1, 0)
+    return dict(pred_masks=pm, scores=scores)
+
+
 def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8):  # LP:325-386
     scores, labels = F.softmax(cls, dim=-1).max(-1)
     nc = cls.shape[-1] - 1
@@ -605,14 +664,20 @@ def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8):
 def eval_seg(sd, input_ids, attention_mask, images, seg_info, class_name_ids=None, cls_indices=None,
              class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None,
              is_thing_list=None, task="panoptic", phi_cfg=PHI_15, return_intermediates=False,
-             obj_thr=0.8, ovl_thr=0.8):
+             obj_thr=0.8, ovl_thr=0.8, region_points=None):
     """Returns list (one dict per image).  NOTE the reference returns after image 0 (LP:1472);
     we process every image the same way.  obj_thr / ovl_thr: the panoptic thresholds the reference hard-codes
     to 0.8 / 0.8 (LP:331-332); other values only in accuracy runs on random weights (oracle/accuracy.py)."""
     feats = swin_forward(sd, "model.vision_tower.", images)  # the reference runs this twice (LP:449, LP:223)
     img_tok = projector_forward(sd, "model.mm_projector.", feats[3])
+    region_features = None
+    if bool((input_ids == REGION_TOKEN_INDEX).any()):   # LP:1346-1349, LP:791-797
+        # region_points: per sample [K,256,2]; None = draw them here from the global CPU generator like the reference
+        if region_points is None:
+            region_points = [sample_region_points(info["instances"].region_masks.tensor) for info in seg_info]
+        region_features = [region_pool(img_tok[b], region_points[b]) for b in range(images.shape[0])]
     seq = assemble_sequence(sd, input_ids, attention_mask, img_tok, class_name_ids, cls_indices,
-                            class_name_embedding_indices, token_refer_id, refer_embedding_indices)
+                            class_name_embedding_indices, token_refer_id, refer_embedding_indices, region_features)
     hidden = phi_forward(sd, "model.", seq["inputs_embeds"], seq["attention_mask"], phi_cfg)
     seg_query = _lin(sd, "seg_query_projector", get_seg_query(hidden, seq["seg_query_mask"]))
     fd = dict(res2=feats[0], res3=feats[1], res4=feats[2], res5=feats[3])
@@ -622,8 +687,11 @@ def eval_seg(sd, input_ids, attention_mask, images, seg_info, class_name_ids=Non
         SEG_emb = _lin(sd, "SEG_token_projector", get_SEG_embedding(hidden, seq["refer_embedding_indices"]))
     if seq["class_name_embedding_indices"] is not None:
         cls_emb = _lin(sd, "class_name_projector", get_class_name_embedding(hidden, seq["class_name_embedding_indices"]))
+    region_emb = None
+    if seq["region_embedding_masks"] is not None:   # LP:1385-1388, LP:302-307
+        region_emb = [_lin(sd, "region_projector", h[m.bool()]) for h, m in zip(hidden, seq["region_embedding_masks"])]
     po = predictor_forward(sd, "predictor.", ms, mask_features, seg_query, SEG_emb, cls_emb,
-                           return_all=return_intermediates)
+                           return_all=return_intermediates, region_embedding_list=region_emb)
     Hi, Wi = images.shape[-2:]
     Hp, Wp = (Hi + 31) // 32 * 32, (Wi + 31) // 32 * 32  # ImageList.from_tensors(size_divisibility=32) LP:1400
     mask_pred = F.interpolate(po["pred_masks"], size=(Hp, Wp), mode="bilinear", align_corners=False)
@@ -653,9 +721,13 @@ def eval_seg(sd, input_ids, attention_mask, images, seg_info, class_name_ids=Non
         if task == "referring":
             r["instances"] = seg_instance_inference(po["pred_SEG_logits"][b].float(), mp.float(),
                                                     po["pred_masks"].shape[1])
+        if task == "region":   # LP:1457-1466 (the reference indexes region_cls_results[0]: it returns after image 0)
+            r["instances"] = region_inference(po["pred_region_logits"][b].float(), mp.float())
+            r["gt"] = sem_seg_postprocess(info["instances"].gt_masks, (oh, ow), height, width)
         results.append(r)
     if return_intermediates:
         return results, dict(feats=feats, img_tok=img_tok, seq=seq, hidden=hidden, seg_query=seg_query,
                              mask_features=mask_features, ms=ms, SEG_emb=SEG_emb, cls_emb=cls_emb, predictor=po,
-                             mask_pred=mask_pred)
+                             mask_pred=mask_pred, region_features=region_features, region_emb=region_emb,
+                             region_points=region_points)
     return results

@@ -59,6 +59,7 @@ SIGNATURES = {
     "psalm_kv_cache_write": ([_c_vp] * 5 + [_c_i] * 7 + [_c_vp], _c_i),
     "psalm_paged_decode_attention": ([_c_vp, ctypes.c_longlong] + [_c_vp] * 5 + [_c_i] * 6 + [_c_vp], _c_i),
     "psalm_patchify": ([_c_vp] * 4 + [_c_i] * 7 + [_c_vp], _c_i),
+    "psalm_region_pool": ([_c_vp] * 4 + [_c_i] * 7 + [_c_vp], _c_i),
     "psalm_patch_merge_layernorm": ([_c_vp] * 4 + [_c_i] * 4 + [ctypes.c_float, _c_i, _c_vp], _c_i),
     "psalm_linear_fused_supported": ([ctypes.c_longlong, _c_i, _c_i, _c_i, ctypes.c_longlong, _c_i], _c_i),
     "psalm_linear_fused": ([_c_vp, ctypes.c_longlong, _c_vp, _c_vp, _c_vp, ctypes.c_longlong, _c_i, _c_i, _c_i,

@@ -332,6 +332,24 @@ def patch_merge_layer_norm(x, H, W, weight, bias, eps=1e-5):
     return y
 
 
+@_on_device
+def region_pool(tokens, points, region_image, h, w):
+    """tokens [B, h*w, C]; points [R, P, 2] fp32 (y, x) in [0, 1]; region_image [R] int32 -> [R, C]: mean over the P
+    points of grid_sample(align_corners=True) on the image's token map (context_cluster.py:333-400)."""
+    for t, n in ((tokens, "tokens"), (points, "points"), (region_image, "region_image")):
+        _chk(t, "region_pool." + n)
+    B, N, C = tokens.shape
+    R, P, two = points.shape
+    if N != h * w or two != 2 or points.dtype != torch.float32 or region_image.dtype != torch.int32 or region_image.numel() != R:
+        raise _lib.PsalmKernelError("region_pool: tokens [B,h*w,C], points [R,P,2] fp32, region_image [R] int32")
+    out = torch.empty((R, C), dtype=tokens.dtype, device=tokens.device)
+    rc = _lib.lib().psalm_region_pool(_lib.ptr(tokens), _lib.ptr(points), _lib.ptr(region_image), _lib.ptr(out), B, h, w, C, R, P,
+                                      _lib.dtype_code(tokens.dtype), _lib.stream_ptr(tokens.device))
+    _lib.check(rc, "psalm_region_pool")
+    _count()
+    return out
+
+
 LINEAR_FUSED = True   # False: library GEMM + separate elementwise pass (A/B runs)
 _EPILOGUES = {"bias": 0, "gelu_erf": 1, "head_major": 2}
 

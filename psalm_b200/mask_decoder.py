@@ -51,7 +51,10 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
         w["dn.w"], w["dn.b"] = cv(g("decoder_norm.weight")), cv(g("decoder_norm.bias"))
         self.query_embed = cv(g("query_embed.weight"))      # forward_woconcat uses query_embed (:619)
         self.level_embed = cv(g("level_embed.weight"))
-        for name, n in (("mask_embed", 3), ("SEG_proj", 2), ("CLASS_proj", 2)):
+        heads = [("mask_embed", 3), ("SEG_proj", 2), ("CLASS_proj", 2)]
+        if prefix + "REGION_proj.layers.0.weight" in sd:    # optional in the checkpoint contract (loader.py)
+            heads.append(("REGION_proj", 2))
+        for name, n in heads:
             for j in range(n):
                 w["%s.%d.w" % (name, j)] = cv(g("%s.layers.%d.weight" % (name, j)))
                 w["%s.%d.b" % (name, j)] = cv(g("%s.layers.%d.bias" % (name, j)))
@@ -72,20 +75,18 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
     # reference-surface entry: NCHW maps in, dict out (mask2former_transformer_decoder.py:488,684-692)
     def __call__(self, x, mask_features, mask=None, seg_query=None, SEG_embedding=None, class_name_embedding=None,
                  region_embedding_list=None):
-        if region_embedding_list is not None:
-            raise NotImplementedError("region prompts are outside this build's scope")
         sizes = [tuple(t.shape[-2:]) for t in x]
         toks = [t.permute(0, 2, 3, 1).reshape(t.shape[0], -1, t.shape[1]).to(self.dtype).contiguous() for t in x]
         B, C, H4, W4 = mask_features.shape
         mf = mask_features.permute(0, 2, 3, 1).reshape(B, H4 * W4, C).to(self.dtype).contiguous()
-        out = self.forward_tokens(toks, sizes, mf, (H4, W4), seg_query, SEG_embedding, class_name_embedding)
+        out = self.forward_tokens(toks, sizes, mf, (H4, W4), seg_query, SEG_embedding, class_name_embedding,
+                                  region_embedding_list=region_embedding_list)
         out["pred_masks"] = out["pred_masks"].view(B, -1, H4, W4)
-        out["pred_region_logits"] = None
         out["aux_outputs"] = []
         return out
 
     def forward_tokens(self, ms_tokens, ms_sizes, mask_features, mf_size, seg_query, SEG_embedding=None,
-                       class_name_embedding=None, return_trace=False, hooks=None):
+                       class_name_embedding=None, return_trace=False, hooks=None, region_embedding_list=None):
         """ms_tokens: 3 maps [B,HW_l,256] (32^2,64^2,128^2 levels); mask_features [B,H4*W4,256];
         seg_query [B,Q,256].  Returns dict(pred_masks [B,Q,H4*W4], pred_class_name_logits, pred_SEG_logits).
         `hooks` (tests only, oracle/parity.py): an object whose before_layer(i, output, bits, row_open, mask_for) may
@@ -179,7 +180,12 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
                 bits, row_open = mask_for((i + 1) % 3, output)
         # final prediction heads (:695-750) — the only ones whose outputs leave the decoder
         dec, me = self._heads_common(output)
-        out = dict(pred_SEG_logits=None, pred_class_name_logits=None)
+        out = dict(pred_SEG_logits=None, pred_class_name_logits=None, pred_region_logits=None)
+        if region_embedding_list is not None:   # [K_b, Q] per sample = region_embedding . REGION_proj(decoder_output) (:737-745)
+            if "REGION_proj.0.w" not in w:
+                raise KeyError("region prompts need predictor.REGION_proj.* in the checkpoint")
+            dr = self._mlp("REGION_proj", 2, dec)
+            out["pred_region_logits"] = [re.to(self.dtype) @ dr[b].t() for b, re in enumerate(region_embedding_list)]
         if SEG_embedding is not None:
             out["pred_SEG_logits"] = torch.bmm(self._mlp("SEG_proj", 2, dec), SEG_embedding.to(self.dtype).transpose(1, 2))
         if class_name_embedding is not None:

@@ -92,6 +92,16 @@ def seg_instance_inference(SEG_cls, mask_pred, topk, sig=None):
     return r
 
 
+def region_inference(region_cls, mask_pred, sig=None):
+    """llava_phi.py:387-400 (region prompts): region_cls [K,Q] -> Instances(pred_masks [Q,H,W], scores [Q,K])."""
+    ms = query_mask_scores(mask_pred, sig)
+    r = Instances(tuple(mask_pred.shape[-2:]))
+    r.pred_masks = (mask_pred > 0).float()
+    r.pred_boxes = Boxes(torch.zeros(mask_pred.shape[0], 4))
+    r.scores = (torch.sigmoid(region_cls.float()) * ms[None, :]).transpose(1, 0)
+    return r
+
+
 def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8, sig=None):
     """llava_phi.py:325-386 -> (panoptic_seg int32 [H,W], segments_info list)."""
     scores, labels = F.softmax(cls.float(), dim=-1).max(-1)

@@ -92,7 +92,7 @@ class PSALM:
         self._check_runtime(device)
         self.use_cuda_graph = use_cuda_graph
         # one fused kernel for the task heads (16-bit storage); fp32 parity runs keep the exact torch path
-        self.fused_postprocess = dtype != torch.float32
+        self._fused_postprocess = dtype != torch.float32
         self.cfg, self.dtype, self.device = cfg, dtype, torch.device(device)
         sd = state_dict
         cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
@@ -101,7 +101,8 @@ class PSALM:
         self.predictor = MultiScaleMaskedTransformerDecoderForOPTPreTrain(sd, "predictor.", cfg.mask, dtype, device)
         self.seg_query = cv(sd["seg_query"])
         self.proj = {n: (cv(sd[n + ".weight"]), cv(sd[n + ".bias"]))
-                     for n in ("seg_query_projector", "SEG_token_projector", "class_name_projector")}
+                     for n in ("seg_query_projector", "SEG_token_projector", "class_name_projector", "region_projector")
+                     if n + ".weight" in sd}     # region_projector is optional in the checkpoint contract (loader.py)
         # lm_head (no bias in the reference, llava_phi.py:191): only the chat / decode path reads it
         self.lm_head = None
         if "lm_head.weight" in sd:
@@ -137,16 +138,27 @@ class PSALM:
         from . import _lib
         _lib.lib()
 
+    @property
+    def fused_postprocess(self):
+        """Fused task-head kernels: 16-bit storage, and not the region task (its head is a [K,Q] score table over the
+        plain thresholded masks, done with torch ops)."""
+        return self._fused_postprocess and not getattr(self, "region_on", False)
+
+    @fused_postprocess.setter
+    def fused_postprocess(self, v):
+        self._fused_postprocess = bool(v)
+
     # ---- configuration (llava_phi.py:268-301) ----------------------------------------------------
     def set_task(self, seg_task):
-        if seg_task not in ("semantic", "instance", "panoptic", "referring"):
-            raise NotImplementedError("SEG_TASK %r (region / video variants are outside this build's scope)" % seg_task)
+        if seg_task not in ("semantic", "instance", "panoptic", "referring", "region"):
+            raise NotImplementedError("SEG_TASK %r (the video variant is outside this build's scope)" % seg_task)
         self.seg_task = seg_task
         self.semantic_on = seg_task in ("semantic", "panoptic")
         self.instance_on = seg_task in ("instance", "panoptic")
         self.panoptic_on = seg_task == "panoptic"
         self.referring_on = seg_task == "referring"
-        self.sem_seg_postprocess_before_inference = self.instance_on or self.panoptic_on or self.referring_on
+        self.region_on = seg_task == "region"
+        self.sem_seg_postprocess_before_inference = self.instance_on or self.panoptic_on or self.referring_on or self.region_on
 
     @classmethod
     def from_state_dict(cls, sd, **kw):
@@ -180,13 +192,22 @@ class PSALM:
         """llava_phi.py:767-971: sentinel ids -> embeddings.  Returns the reference's tuple
         (input_ids=None, attention_mask, past_key_values, inputs_embeds, labels, seg_query_mask,
          class_name_embedding_indices, region_embedding_masks, refer_embedding_indices) for the image-prefill case."""
-        if instances is not None:
-            raise NotImplementedError("<region> prompts are outside this build's scope (SURVEY.md section 8 f3)")
         with self._precision_scope():
             img_tok = self.encode_images(images.to(self.device))
         plan = self.make_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
-                              class_name_embedding_indices, token_refer_id, refer_embedding_indices).to(self.device)
-        embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query)
+                              class_name_embedding_indices, token_refer_id, refer_embedding_indices)
+        region_mask = None
+        region_feat = None
+        if plan.region_pos is not None:    # llava_phi.py:791-797: region features from the instances' region masks
+            if instances is None:
+                raise ValueError("<region> tokens in the prompt need `instances` with region_masks (llava_phi.py:791-792)")
+            from .region import region_inputs
+            plan.region_points, plan.region_image, counts = region_inputs([dict(instances=i) for i in instances])
+            assert counts == plan.region_counts, "the munber of <region> tokens and regions needs to be same"
+        plan = plan.to(self.device)
+        if plan.region_pos is not None:
+            region_feat = self._region_features(img_tok, plan)
+        embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query, region_feat)
         B, T = plan.B, plan.T
         flat = lambda pos: torch.zeros(B * T, device=self.device).index_fill_(0, pos, 1.0).view(B, T)   # noqa: E731
         seg_query_mask = flat(plan.seg_pos)
@@ -195,7 +216,18 @@ class PSALM:
             cls_idx = ((plan.cls_pool > 0).float() * torch.arange(1, plan.cls_pool.shape[1] + 1, device=self.device)
                        .view(1, -1, 1)).sum(1).long()
         ref_idx = (plan.refer_pool[:, 0] > 0).long() if plan.refer_pool is not None else None
-        return None, plan.attention_mask, past_key_values, embeds, labels, seg_query_mask, cls_idx, None, ref_idx
+        if plan.region_pos is not None:
+            region_mask = flat(plan.region_pos)
+        return None, plan.attention_mask, past_key_values, embeds, labels, seg_query_mask, cls_idx, region_mask, ref_idx
+
+    def _region_features(self, img_tok, plan):
+        """[R, hidden] pooled region features (region_pooling, context_cluster.py:333-400) from the projector tokens."""
+        from . import kernels
+        n_img = img_tok.shape[1]
+        h = w = int(round(n_img ** 0.5))
+        if h * w != n_img:      # context_cluster.py:355 takes h = w = int(sqrt(n)): square maps only
+            raise ValueError("region prompts need a square projector map (got %d tokens)" % n_img)
+        return kernels.region_pool(img_tok.contiguous(), plan.region_points, plan.region_image, h, w)
 
     # ---- LlavaMetaForCausalLM surface --------------------------------------------------------------
     def get_model(self):
@@ -230,7 +262,8 @@ class PSALM:
         h5, w5 = sizes[3]
         res5 = toks[3].view(toks[3].shape[0], h5, w5, -1).permute(0, 3, 1, 2)
         img_tok = self.model.mm_projector(res5)                                        # [B,n_img,hidden]
-        embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query)
+        region_feat = self._region_features(img_tok, plan) if plan.region_pos is not None else None
+        embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query, region_feat)
         hidden = self.model.phi(embeds, plan.attention_mask if plan.any_padding else None)
         seg_q = F.linear(SEQ.gather_seg_query(plan, hidden), *self.proj["seg_query_projector"])
         SEG_emb = cls_emb = None
@@ -238,10 +271,18 @@ class PSALM:
             SEG_emb = F.linear(SEQ.pool(plan.refer_pool, hidden), *self.proj["SEG_token_projector"])
         if plan.cls_pool is not None:
             cls_emb = F.linear(SEQ.pool(plan.cls_pool, hidden), *self.proj["class_name_projector"])
+        region_emb = None
+        if plan.region_pos is not None:     # llava_phi.py:1385-1388: hidden states at the <region> rows -> region_projector
+            if "region_projector" not in self.proj:
+                raise KeyError("region prompts need region_projector.* in the checkpoint")
+            rows = F.linear(SEQ.gather_region_rows(plan, hidden), *self.proj["region_projector"])
+            region_emb = list(torch.split(rows, list(plan.region_counts), 0))
         mask_features, ms, ms_sizes = self.pixel_decoder.forward_tokens(toks, sizes)
-        out = self.predictor.forward_tokens(ms, ms_sizes, mask_features, sizes[0], seg_q, SEG_emb, cls_emb)
+        out = self.predictor.forward_tokens(ms, ms_sizes, mask_features, sizes[0], seg_q, SEG_emb, cls_emb,
+                                            region_embedding_list=region_emb)
         out["mask_size"] = sizes[0]
         if trace is not None:
+            trace.update(region_features=region_feat, region_emb=region_emb)
             trace.update(swin=toks, swin_sizes=sizes, img_tok=img_tok, embeds=embeds, hidden=hidden, seg_query=seg_q,
                          SEG_emb=SEG_emb, cls_emb=cls_emb, mask_features=mask_features, ms=ms, ms_sizes=ms_sizes)
         return out
@@ -388,11 +429,11 @@ class PSALM:
     def eval_seg(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
                  use_cache=None, output_attentions=None, output_hidden_states=None, images=None, return_dict=None,
                  seg_info=None, class_name_ids=None, class_name_embedding_indices=None, cls_indices=None,
-                 token_refer_id=None, refer_embedding_indices=None, is_thing_list=None):
+                 token_refer_id=None, refer_embedding_indices=None, is_thing_list=None, region_points=None):
         if self.panoptic_on:
             assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
             self.is_thing_list = is_thing_list
-        return self.eval_seg_async(input_ids=input_ids, attention_mask=attention_mask, images=images, seg_info=seg_info,
+        return self.eval_seg_async(region_points=region_points, input_ids=input_ids, attention_mask=attention_mask, images=images, seg_info=seg_info,
                                    class_name_ids=class_name_ids, class_name_embedding_indices=class_name_embedding_indices,
                                    cls_indices=cls_indices, token_refer_id=token_refer_id,
                                    refer_embedding_indices=refer_embedding_indices, is_thing_list=is_thing_list).result()
@@ -400,10 +441,11 @@ class PSALM:
     @torch.no_grad()
     def eval_seg_async(self, input_ids=None, attention_mask=None, images=None, seg_info=None, class_name_ids=None,
                        class_name_embedding_indices=None, cls_indices=None, token_refer_id=None,
-                       refer_embedding_indices=None, is_thing_list=None, lane=0):
+                       refer_embedding_indices=None, is_thing_list=None, lane=0, region_points=None):
         """Submit one `eval_seg` call and return a `PendingSeg`; `.result()` gives what `eval_seg` returns.  `lane`
         selects an independent CUDA graph + static output buffers, so that a caller alternating lanes 0 / 1 can finish
-        batch k (host merge, read-back) while the device already runs batch k+1."""
+        batch k (host merge, read-back) while the device already runs batch k+1.  `region_points`: optional per-sample
+        [K,256,2] sample points for <region> prompts (default: drawn like the reference, psalm_b200/region.py)."""
         if self.panoptic_on:
             assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
             self.is_thing_list = is_thing_list
@@ -417,8 +459,16 @@ class PSALM:
             images_d = images.to(self.device, non_blocking=True)
         plan = self._cached_plan(input_ids, attention_mask, images.shape[-2:], class_name_ids, cls_indices,
                                  class_name_embedding_indices, token_refer_id, refer_embedding_indices)
+        has_regions = plan.region_pos is not None
+        if has_regions:   # llava_phi.py:1346-1349: the regions come with the request (seg_info[i]['instances'].region_masks)
+            import copy
+            from .region import region_inputs
+            pts, img, counts = region_inputs(seg_info, region_points)
+            assert counts == plan.region_counts, "the munber of <region> tokens and regions needs to be same"   # llava_phi.py:593
+            plan = copy.copy(plan)
+            plan.region_points, plan.region_image = pts.to(self.device), img.to(self.device)
         fused, boxes = self._fused_applies(images.shape[-2:], seg_info)
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and not has_regions:   # the number of regions varies per request: eager launches
             out = self.forward_core_graphed(images_d, plan, lane=lane, fuse_post=fused)
         else:
             out = self.forward_core(images_d, plan)
@@ -540,5 +590,10 @@ class PSALM:
             if self.referring_on:
                 r["instances"] = PP.seg_instance_inference(out["pred_SEG_logits"][b].float(), mp,
                                                            self.test_topk_per_image, sig)
+            if self.region_on:   # llava_phi.py:1457-1466
+                r["instances"] = PP.region_inference(out["pred_region_logits"][b].float(), mp, sig)
+                gt = info["instances"].gt_masks
+                gt = gt.tensor if hasattr(gt, "tensor") else gt
+                r["gt"] = PP.sem_seg_postprocess(gt.to(mp.device).float(), (oh, ow), height, width)
             results.append(r)
         return results

@@ -37,12 +37,17 @@ class SequencePlan:
     refer_pool: Optional[torch.Tensor]  # [B,1,T] fp32, or None
     n_img: int
     n_q: int
+    region_pos: Optional[torch.Tensor] = None   # [R] int64 flat rows of the <region> tokens (sample-major, prompt order)
+    region_counts: Optional[tuple] = None        # regions per sample
+    region_points: Optional[torch.Tensor] = None  # [R,P,2] fp32 sample points (y, x) in [0,1], set by the caller
+    region_image: Optional[torch.Tensor] = None   # [R] int32 image index of every region
 
     def to(self, device):
         mv = lambda t: None if t is None else t.to(device, non_blocking=True)  # noqa: E731
         return SequencePlan(self.B, self.T, mv(self.tok_ids), mv(self.img_pos), mv(self.seg_pos), mv(self.pad_pos),
                             mv(self.attention_mask), self.any_padding, mv(self.cls_pool), mv(self.refer_pool),
-                            self.n_img, self.n_q)
+                            self.n_img, self.n_q, mv(self.region_pos), self.region_counts, mv(self.region_points),
+                            mv(self.region_image))
 
 
 def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_indices=None,
@@ -51,8 +56,7 @@ def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_i
     ids_all = input_ids.cpu().numpy()
     B, T0 = ids_all.shape
     am_all = np.ones((B, T0), bool) if attention_mask is None else attention_mask.cpu().numpy().astype(bool)
-    if (ids_all == REGION_TOKEN_INDEX).any():
-        raise NotImplementedError("<region> prompts (visual-prompt task) are outside this build's scope (SURVEY.md §2 #8)")
+    has_region = bool((ids_all == REGION_TOKEN_INDEX).any())
     rows = []
     for b in range(B):
         ids = ids_all[b]
@@ -74,7 +78,7 @@ def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_i
         refer = token_refer_id[b].cpu().numpy() if token_refer_id is not None else None
         cei = class_name_embedding_indices[b].cpu().numpy() if class_name_embedding_indices is not None else None
         rei = refer_embedding_indices[b].cpu().numpy() if refer_embedding_indices is not None else None
-        tok, kind, cidx, ridx = [], [], [], []   # kind: 1 text, 2 image, 3 seg
+        tok, kind, cidx, ridx = [], [], [], []   # kind: 1 text, 2 image, 3 seg, 4 region feature
         special = np.nonzero(ids < 0)[0]
         prev_end = 0
         cls_i = 0
@@ -99,6 +103,8 @@ def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_i
             elif t == REFER_TOKEN_INDEX:
                 tk = refer
                 n, k, cv, rv = len(tk), 1, 0, 1
+            elif t == REGION_TOKEN_INDEX:   # one row per region, filled with its pooled feature (llava_phi.py:684-703)
+                n, k, tk, cv, rv = 1, 4, np.zeros(1, np.int64), 0, 0
             else:
                 raise ValueError("unknown sentinel id %d" % t)
             tok.append(tk); kind.append(np.full(n, k)); cidx.append(np.full(n, cv)); ridx.append(np.full(n, rv))
@@ -113,7 +119,7 @@ def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_i
     attn = np.zeros((B, T), bool)
     cls_idx = np.zeros((B, T), np.int64)
     ref_idx = np.zeros((B, T), np.int64)
-    img_pos, seg_pos, pad_pos = [], [], []
+    img_pos, seg_pos, pad_pos, region_pos, region_counts = [], [], [], [], []
     for b, (tok, kind, cidx, ridx, am) in enumerate(rows):
         n = len(tok)
         tok_ids[b, :n] = np.where(kind == 1, tok, 0)
@@ -122,6 +128,8 @@ def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_i
         ref_idx[b, :n] = ridx
         img_pos.append(b * T + np.nonzero(kind == 2)[0])
         seg_pos.append(b * T + np.nonzero(kind == 3)[0])
+        region_pos.append(b * T + np.nonzero(kind == 4)[0])
+        region_counts.append(int((kind == 4).sum()))
         pad_pos.append(b * T + np.arange(n, T))
     pad_pos = np.concatenate(pad_pos)
     cls_pool = refer_pool = None
@@ -143,16 +151,21 @@ def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_i
     return SequencePlan(B, T, ft(tok_ids), ft(np.concatenate(img_pos)), ft(np.concatenate(seg_pos)),
                         ft(pad_pos) if len(pad_pos) else None, ft(attn), any_padding,
                         ft(cls_pool) if cls_pool is not None else None,
-                        ft(refer_pool) if refer_pool is not None else None, n_img, n_q)
+                        ft(refer_pool) if refer_pool is not None else None, n_img, n_q,
+                        ft(np.concatenate(region_pos)) if has_region else None,
+                        tuple(region_counts) if has_region else None)
 
 
-def materialize_embeds(plan, embed_tokens, image_tokens, seg_query):
-    """plan on device; embed_tokens [V,C]; image_tokens [B,n_img,C]; seg_query [n_q,C] -> inputs_embeds [B,T,C]."""
+def materialize_embeds(plan, embed_tokens, image_tokens, seg_query, region_features=None):
+    """plan on device; embed_tokens [V,C]; image_tokens [B,n_img,C]; seg_query [n_q,C]; region_features [R,C] (one
+    row per <region> token, plan.region_pos order) -> inputs_embeds [B,T,C]."""
     B, T = plan.B, plan.T
     C = embed_tokens.shape[1]
     flat = embed_tokens.index_select(0, plan.tok_ids.view(-1))
     flat.index_copy_(0, plan.img_pos, image_tokens.reshape(-1, C).to(flat.dtype))
     flat.index_copy_(0, plan.seg_pos, seg_query.to(flat.dtype).repeat(B, 1))
+    if plan.region_pos is not None:
+        flat.index_copy_(0, plan.region_pos, region_features.to(flat.dtype))
     if plan.pad_pos is not None:
         flat.index_fill_(0, plan.pad_pos, 0)   # right padding rows are zeros (llava_phi.py:878-883)
     return flat.view(B, T, C)
@@ -166,3 +179,8 @@ def gather_seg_query(plan, hidden):
 def pool(pool_matrix, hidden):
     """[B,n,T] averaging matrix x [B,T,C] -> [B,n,C] (class-name / [SEG] mean pooling)."""
     return torch.bmm(pool_matrix.to(hidden.dtype), hidden)
+
+
+def gather_region_rows(plan, hidden):
+    """hidden [B,T,C] -> [R,C] hidden states at the <region> positions (get_region_embedding, llava_phi.py:302-307)."""
+    return hidden.reshape(plan.B * plan.T, -1).index_select(0, plan.region_pos)

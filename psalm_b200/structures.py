@@ -10,6 +10,16 @@ class Boxes:
         return self.tensor.shape[0]
 
 
+class BitMasks:
+    """detectron2.structures.BitMasks stand-in: `.tensor` [N,H,W] bool (region prompts, llava_phi.py:792)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+
 class Instances:
     def __init__(self, image_size, **fields):
         object.__setattr__(self, "_image_size", tuple(image_size))

@@ -89,7 +89,7 @@ def synth_state_dict(cfg: PsalmConfig = PsalmConfig(), seed=0, include_lm_head=F
 
 
 def synth_inputs(batch=1, height=1024, width=1024, task="panoptic", n_classes=134, seed=1, text_len=(12, 8, 9),
-                 refer_len=12, vocab_hi=50000, ragged=False):
+                 refer_len=12, vocab_hi=50000, ragged=False, n_regions=3):
     """Synthetic request in the reference's input contract.
 
     panoptic / instance / semantic: 12 text ids + <image> + 8 ids + n_classes x (<cls>, one id) + 9 ids +
@@ -129,6 +129,14 @@ def synth_inputs(batch=1, height=1024, width=1024, task="panoptic", n_classes=13
             ids_list.append(ids)
             refer.append(torch.tensor(rnd(n) + [SEG_MARKER_ID], dtype=torch.long))
         out["token_refer_id"] = refer
+    elif task == "region":   # train_datasets.py:339-341: text <image> text (<region> text) x K text <seg> text
+        for b in range(batch):
+            k = n_regions + (b if ragged else 0)
+            ids = rnd(text_len[0]) + [-200] + rnd(text_len[1])
+            for _ in range(k):
+                ids += [-203] + rnd(1)
+            ids += rnd(text_len[2]) + [-201] + rnd(1)
+            ids_list.append(ids)
     else:
         raise ValueError(task)
     T = max(len(i) for i in ids_list)
@@ -145,12 +153,27 @@ def synth_inputs(batch=1, height=1024, width=1024, task="panoptic", n_classes=13
         cei = torch.zeros_like(input_ids)
         cei[input_ids == -202] = 1
         out["class_name_embedding_indices"] = cei
-    else:
+    elif task == "referring":
         rei = torch.zeros_like(input_ids)
         rei[input_ids == -204] = 1
         out["refer_embedding_indices"] = rei
     out["seg_info"] = [dict(padding_mask=torch.zeros(height, width, dtype=torch.bool), height=height, width=width)
                        for _ in range(batch)]
+    if task == "region":   # instances.region_masks (BitMasks-like .tensor) and gt_masks, one per <region> token
+        from .structures import BitMasks, Instances
+        for b in range(batch):
+            k = int((input_ids[b] == -203).sum())
+            rm = torch.zeros(k, height, width, dtype=torch.bool)
+            for j in range(k):   # rectangles of very different areas: < 256 pixels (repeat path) and > 256 (randperm path)
+                hh = 3 + 7 * j if j % 2 == 0 else height // 3 + 5 * j
+                ww = 4 + 5 * j if j % 2 == 0 else width // 4 + 3 * j
+                y0 = int(torch.randint(0, height - hh + 1, (1,), generator=g))
+                x0 = int(torch.randint(0, width - ww + 1, (1,), generator=g))
+                rm[j, y0:y0 + hh, x0:x0 + ww] = True
+            inst = Instances((height, width))
+            inst.region_masks = BitMasks(rm)
+            inst.gt_masks = rm.float()
+            out["seg_info"][b]["instances"] = inst
     if task == "panoptic":
         out["is_thing_list"] = [True] * min(80, n_classes - 1) + [False] * max(0, n_classes - 1 - 80)
     return out

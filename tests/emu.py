@@ -176,7 +176,7 @@ def install(monkeypatch):
     from psalm_b200 import kernels
     for name in ("window_attention", "rotary_inplace", "causal_attention", "cross_attention", "mask_logits",
                  "bilinear_tokens", "attn_mask_bits", "msda_encoder_fused", "add_layer_norm", "group_norm_tokens", "mask_bits", "patchify", "masked_cross_attention", "kv_cache_write",
-                 "paged_decode_attention", "linear_fused_supported", "patch_merge_layer_norm"):
+                 "paged_decode_attention", "linear_fused_supported", "patch_merge_layer_norm", "region_pool"):
         monkeypatch.setattr(kernels, name, globals()[name])
 
 
@@ -229,3 +229,13 @@ def patch_merge_layer_norm(x, H, W, weight, bias, eps=1e-5):
     xm = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1)
     xm = xm.reshape(B, -1, 4 * C)
     return add_layer_norm(xm.contiguous(), weight, bias, eps)
+
+
+def region_pool(tokens, points, region_image, h, w):
+    outs = []
+    for r in range(points.shape[0]):
+        fmap = tokens[int(region_image[r])].float().view(h, w, -1).permute(2, 0, 1)[None]
+        grid = (2.0 * points[r:r + 1].flip(dims=(2,)) - 1.0).unsqueeze(2)
+        fea = F.grid_sample(fmap, grid.float(), align_corners=True).squeeze(3)        # [1,C,P]
+        outs.append(fea.mean(-1))
+    return torch.cat(outs, 0).to(tokens.dtype)

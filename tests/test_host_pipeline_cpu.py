@@ -90,3 +90,69 @@ def test_host_pipeline_matches_golden(monkeypatch, golden, case):
         sc = res[0]["instances"].scores
         order = torch.argsort(sc, descending=True, stable=True)
         assert np.allclose(sc[order].numpy(), g["inst_scores_sorted"], rtol=1e-3, atol=1e-4)
+
+
+def test_region_sequence_plan_matches_oracle():
+    """<region> rows: build_plan + materialize_embeds == oracle.assemble_sequence with region features, and the
+    region-embedding rows gathered after the LLM are the masked rows of the reference (llava_phi.py:302-307)."""
+    inp = synth.synth_inputs(batch=3, height=64, width=64, task="region", seed=4, ragged=True)
+    g = torch.Generator().manual_seed(0)
+    C, n_img, n_q = 32, 4, 100
+    sd = {"model.embed_tokens.weight": torch.randn(51200, C, generator=g), "seg_query": torch.randn(n_q, C, generator=g)}
+    img = torch.randn(3, n_img, C, generator=g)
+    counts = [int((inp["input_ids"][b] == -203).sum()) for b in range(3)]
+    feats = [torch.randn(k, 1, C, generator=g) for k in counts]
+    ref = O.assemble_sequence(sd, inp["input_ids"], inp["attention_mask"], img, region_features=feats)
+    plan = SEQ.build_plan(inp["input_ids"], inp["attention_mask"], n_img, n_q)
+    assert plan.region_counts == tuple(counts)
+    emb = SEQ.materialize_embeds(plan, sd["model.embed_tokens.weight"], img, sd["seg_query"], torch.cat(feats, 0).squeeze(1))
+    assert torch.equal(emb, ref["inputs_embeds"]) and torch.equal(plan.attention_mask, ref["attention_mask"])
+    hidden = torch.randn(3, plan.T, C, generator=g)
+    want = torch.cat([h[m.bool()] for h, m in zip(hidden, ref["region_embedding_masks"])], 0)
+    assert torch.equal(SEQ.gather_region_rows(plan, hidden), want)
+
+
+def test_region_points_follow_the_reference_rng_stream():
+    """psalm_b200.region.sample_region_points makes the reference's draws in the reference's order
+    (context_cluster.py:31-40): with the same seed it returns the oracle's points (which are pinned to the reference
+    by tests/golden/e2e_region_192x192_b1.npz, generated with the reference's region_pooling under the same seed)."""
+    from psalm_b200 import region as R
+    inp = synth.synth_inputs(batch=1, height=192, width=192, task="region", seed=10)
+    masks = inp["seg_info"][0]["instances"].region_masks.tensor
+    torch.manual_seed(1234)
+    a = R.sample_region_points(masks)
+    torch.manual_seed(1234)
+    b = O.sample_region_points(masks)
+    assert a.shape == (masks.shape[0], 256, 2) and torch.equal(a, b.float())
+    # small masks: every mask pixel is present (plus repeats); large masks: 256 distinct pixels of the mask
+    for m, p in zip(masks, a):
+        yx = (p * torch.tensor([192.0, 192.0])).round().long()
+        assert bool(m[yx[:, 0], yx[:, 1]].all())
+        n = int(m.sum())
+        assert len({tuple(t) for t in yx.tolist()}) == min(n, 256)
+
+
+def test_region_host_pipeline_matches_reference_golden(monkeypatch, golden):
+    """The whole region path with emulated kernels against the fixture the UNMODIFIED reference produced
+    (oracle/gen_golden_modules.py, case region_192x192): region logits [K,Q], scores [Q,K], thresholded masks, gt."""
+    H = W = 192
+    sd = synth.synth_state_dict(SMALL, seed=9)
+    inp = synth.synth_inputs(batch=1, height=H, width=W, task="region", seed=10)
+    m = _emu_model(monkeypatch, sd, "region")
+    g = golden("e2e_region_192x192_b1.npz")
+    pts = [torch.from_numpy(g["region_points_0"])]
+    plan = m.make_plan(inp["input_ids"], inp["attention_mask"], (H, W))
+    from psalm_b200.region import region_inputs
+    plan.region_points, plan.region_image, counts = region_inputs(inp["seg_info"], pts)
+    assert counts == plan.region_counts
+    out = m.forward_core(inp["images"], plan)
+    rl = out["pred_region_logits"][0].numpy()
+    assert rl.shape == g["pred_region_logits_0"].shape
+    assert np.abs(rl - g["pred_region_logits_0"]).max() / np.abs(g["pred_region_logits_0"]).max() < 2e-3
+    res = m.post_process(out, (H, W), inp["seg_info"])
+    inst = res[0]["instances"]
+    assert np.allclose(inst.scores.numpy(), g["region_scores"], rtol=2e-3, atol=2e-4)
+    area = inst.pred_masks.flatten(1).sum(1).numpy()
+    assert np.abs(area - g["region_mask_area"]).max() <= 2          # |logit| ~ 0 ties only
+    gt = res[0]["gt"].reshape(-1)[torch.from_numpy(g["region_gt_idx"])].numpy()
+    assert np.allclose(gt, g["region_gt"], atol=1e-6)

@@ -1,0 +1,91 @@
+"""Region prompts on the GPU: the point-sampling / pooling kernel against
+F.grid_sample(align_corners=True) (context_cluster.py:43-68, :355-392), and the whole region path of PSALM.eval_seg
+against the fixture the UNMODIFIED reference produced and against the oracle (fp32 within 1e-3; 16-bit tracks)."""
+import numpy as np
+import pytest
+import torch
+
+import emu
+from psalm_b200 import synth
+from psalm_b200.layout import PhiConfig, PsalmConfig
+
+pytestmark = pytest.mark.gpu
+SMALL = PsalmConfig(phi=PhiConfig(hidden=256, layers=2, heads=4, inter=1024))
+SMALL_O = dict(hidden=256, layers=2, heads=4, inter=1024, eps=1e-5, theta=10000.0, rotary_frac=0.5)
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 2e-6), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)], ids=["f32", "f16", "bf16"])
+@pytest.mark.parametrize("h,w,C", [(6, 6, 256), (32, 32, 2048), (7, 5, 64)])
+def test_region_pool_kernel(dt, tol, h, w, C):
+    from psalm_b200 import kernels
+    g = torch.Generator().manual_seed(h * w + C)
+    B, R, P = 3, 5, 256
+    tokens = torch.randn(B, h * w, C, generator=g).to(dt)
+    points = torch.rand(R, P, 2, generator=g)
+    points[0, :4] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.999999, 0.5]])    # map corners / last row
+    img = torch.tensor([0, 2, 1, 1, 0], dtype=torch.int32)
+    ref = emu.region_pool(tokens.float(), points, img, h, w)
+    out = kernels.region_pool(tokens.cuda(), points.cuda(), img.cuda(), h, w)
+    assert out.shape == (R, C) and out.dtype == dt
+    err = (out.float().cpu() - ref).abs().max() / ref.abs().max()
+    assert err < tol, float(err)
+
+
+def _run(dtype, inp, sd, pts):
+    from psalm_b200.psalm import PSALM
+    m = PSALM(sd, SMALL, dtype, "cuda", "region", use_cuda_graph=(dtype != torch.float32))   # graphs are skipped for regions
+    res = m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                     seg_info=inp["seg_info"], region_points=pts)
+    torch.cuda.synchronize()
+    return m, res
+
+
+def test_region_eval_seg_fp32_matches_reference_golden(golden):
+    H = W = 192
+    sd = synth.synth_state_dict(SMALL, seed=9)
+    inp = synth.synth_inputs(batch=1, height=H, width=W, task="region", seed=10)
+    g = golden("e2e_region_192x192_b1.npz")
+    _, res = _run(torch.float32, inp, sd, [torch.from_numpy(g["region_points_0"])])
+    inst = res[0]["instances"]
+    assert tuple(inst.scores.shape) == g["region_scores"].shape          # [Q, K]
+    assert np.allclose(inst.scores.cpu().numpy(), g["region_scores"], rtol=1e-3, atol=1e-4)
+    area = inst.pred_masks.flatten(1).sum(1).cpu().numpy()
+    assert np.abs(area - g["region_mask_area"]).max() <= 2
+    gt = res[0]["gt"].reshape(-1)[torch.from_numpy(g["region_gt_idx"]).cuda()].cpu().numpy()
+    assert np.allclose(gt, g["region_gt"], atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.float16, 4e-2), (torch.bfloat16, 2.5e-1)], ids=["f32", "f16", "bf16"])
+def test_region_eval_seg_batch2_vs_oracle(dtype, tol):
+    """Two images with different numbers of regions (3 and 4, ragged prompts), default point sampling: seeding the
+    global generator like the reference gives the oracle's points; region logits [K,Q] and scores [Q,K] are compared."""
+    from oracle import psalm_oracle as O
+    sd = synth.synth_state_dict(SMALL, seed=11)
+    inp = synth.synth_inputs(batch=2, height=160, width=160, task="region", seed=12, ragged=True)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        ores, it = O.eval_seg(sd, inp["input_ids"], inp["attention_mask"], inp["images"], inp["seg_info"], task="region",
+                              phi_cfg=SMALL_O, return_intermediates=True)
+    torch.manual_seed(77)
+    m, res = _run(dtype, inp, sd, None)          # points drawn by psalm_b200.region from the same stream
+    plan = m.make_plan(inp["input_ids"], inp["attention_mask"], (160, 160))
+    assert plan.region_counts == (3, 4)
+    for b in range(2):
+        a, o = res[b]["instances"].scores.float().cpu(), ores[b]["instances"]["scores"]
+        assert a.shape == o.shape == (100, 3 + b)
+        assert (a - o).norm() / o.norm() < tol, (b, float((a - o).norm() / o.norm()))
+        if dtype == torch.float32:
+            assert torch.equal(res[b]["instances"].pred_masks.cpu() > 0, ores[b]["instances"]["pred_masks"] > 0) or \
+                (res[b]["instances"].pred_masks.cpu() != ores[b]["instances"]["pred_masks"]).float().mean() < 1e-5
+            assert torch.allclose(res[b]["gt"].cpu(), ores[b]["gt"], atol=1e-6)
+
+
+def test_region_prompt_errors():
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=11)
+    inp = synth.synth_inputs(batch=1, height=96, width=96, task="region", seed=3)
+    m = PSALM(sd, SMALL, torch.bfloat16, "cuda", "region")
+    wrong = [torch.rand(2, 256, 2)]                                       # 2 point sets for 3 <region> tokens
+    with pytest.raises(AssertionError, match="munber of <region> tokens"):   # the reference's message (llava_phi.py:593)
+        m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                   seg_info=inp["seg_info"], region_points=wrong)
