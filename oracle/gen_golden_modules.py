@@ -40,7 +40,9 @@ def rel(a, b):
 
 
 def build_ref(task, seed=0):
-    m = ref_shims.build_reference_psalm(task, num_hidden_layers=SMALL_PHI.layers, hidden_size=SMALL_PHI.hidden)
+    davis = task == "davis"
+    task = "region" if davis else task
+    m = ref_shims.build_reference_psalm(task, num_hidden_layers=SMALL_PHI.layers, hidden_size=SMALL_PHI.hidden, davis=davis)
     sd = synth.synth_state_dict(SMALL, seed=seed, include_lm_head=True)
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
@@ -51,9 +53,11 @@ def build_ref(task, seed=0):
 
 def run_case(task, H, W, n_classes, seed, batch=1, ragged=False):
     m, sd = build_ref(task, seed)
-    inp = synth.synth_inputs(batch=batch, height=H, width=W, task=task, n_classes=n_classes, seed=seed + 1,
-                             ragged=ragged)
     name = "e2e_%s_%dx%d_b%d" % (task, H, W, batch)
+    davis = task == "davis"     # PSALMForDAVISEval: region prompts pooled from a visual-prompt frame
+    task = "region" if davis else task
+    inp = synth.synth_inputs(batch=batch, height=H, width=W, task=task, n_classes=n_classes, seed=seed + 1,
+                             ragged=ragged, visual_prompt_frame=davis)
     gold = {}
     # ---- reference, module by module (hooks on the real modules) ----
     caps = {}
@@ -87,7 +91,7 @@ def run_case(task, H, W, n_classes, seed, batch=1, ragged=False):
     kw = dict(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
               seg_info=inp["seg_info"], labels=inp["input_ids"].clone())
     for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "token_refer_id",
-              "refer_embedding_indices", "is_thing_list"):
+              "refer_embedding_indices", "is_thing_list", "vp_images"):
         if k in inp:
             kw[k] = inp[k]
     if task == "region":
@@ -105,7 +109,7 @@ def run_case(task, H, W, n_classes, seed, batch=1, ragged=False):
                           token_refer_id=inp.get("token_refer_id"),
                           refer_embedding_indices=inp.get("refer_embedding_indices"),
                           is_thing_list=inp.get("is_thing_list"), task=task, phi_cfg=SMALL_PHI_ORACLE,
-                          return_intermediates=True)
+                          return_intermediates=True, vp_images=inp.get("vp_images"))
     rep = {}
     swin_ref = caps["swin"][0]
     for i in range(4):
@@ -186,6 +190,7 @@ CASES = [
     ("referring", 192, 192, 0, 5, 1, False),
     ("panoptic", 96, 128, 7, 7, 2, True),        # batch 2, ragged prompts -> right padding + attention mask
     ("region", 192, 192, 0, 9, 1, False),        # <region> prompts: point-sampled region features + REGION_proj head
+    ("davis", 192, 192, 0, 13, 1, False),        # PSALMForDAVISEval: the regions come from a visual-prompt frame
 ]
 
 

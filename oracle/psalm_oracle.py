@@ -664,18 +664,24 @@ def panoptic_inference(cls, mask_pred, is_thing_list, obj_thr=0.8, ovl_thr=0.8):
 def eval_seg(sd, input_ids, attention_mask, images, seg_info, class_name_ids=None, cls_indices=None,
              class_name_embedding_indices=None, token_refer_id=None, refer_embedding_indices=None,
              is_thing_list=None, task="panoptic", phi_cfg=PHI_15, return_intermediates=False,
-             obj_thr=0.8, ovl_thr=0.8, region_points=None):
+             obj_thr=0.8, ovl_thr=0.8, region_points=None, vp_images=None):
     """Returns list (one dict per image).  NOTE the reference returns after image 0 (LP:1472);
     we process every image the same way.  obj_thr / ovl_thr: the panoptic thresholds the reference hard-codes
-    to 0.8 / 0.8 (LP:331-332); other values only in accuracy runs on random weights (oracle/accuracy.py)."""
+    to 0.8 / 0.8 (LP:331-332); other values only in accuracy runs on random weights (oracle/accuracy.py).
+    vp_images: the DAVIS variant (PSALMForDAVISEval, LP:1477-1520, :1662-1670): the region features are pooled from the
+    projector map of a SECOND image (the visual-prompt frame) with `instances.vp_region_masks`."""
     feats = swin_forward(sd, "model.vision_tower.", images)  # the reference runs this twice (LP:449, LP:223)
     img_tok = projector_forward(sd, "model.mm_projector.", feats[3])
     region_features = None
     if bool((input_ids == REGION_TOKEN_INDEX).any()):   # LP:1346-1349, LP:791-797
         # region_points: per sample [K,256,2]; None = draw them here from the global CPU generator like the reference
+        attr = "region_masks" if vp_images is None else "vp_region_masks"   # LP:792 / LP:1664
         if region_points is None:
-            region_points = [sample_region_points(info["instances"].region_masks.tensor) for info in seg_info]
-        region_features = [region_pool(img_tok[b], region_points[b]) for b in range(images.shape[0])]
+            region_points = [sample_region_points(getattr(info["instances"], attr).tensor) for info in seg_info]
+        src_tok = img_tok
+        if vp_images is not None:   # LP:1665
+            src_tok = projector_forward(sd, "model.mm_projector.", swin_forward(sd, "model.vision_tower.", vp_images)[3])
+        region_features = [region_pool(src_tok[b], region_points[b]) for b in range(images.shape[0])]
     seq = assemble_sequence(sd, input_ids, attention_mask, img_tok, class_name_ids, cls_indices,
                             class_name_embedding_indices, token_refer_id, refer_embedding_indices, region_features)
     hidden = phi_forward(sd, "model.", seq["inputs_embeds"], seq["attention_mask"], phi_cfg)

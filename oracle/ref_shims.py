@@ -242,10 +242,14 @@ def load_mask_cfg(seg_task="panoptic", name="maskformer2_swin_base_384_bs16_50ep
     return cfg
 
 
-def build_reference_psalm(seg_task="panoptic", num_hidden_layers=None, hidden_size=None, **cfg_over):
-    """Construct the reference `PSALM` (llava_phi.py:146) on CPU, fp32, eval mode."""
+def build_reference_psalm(seg_task="panoptic", num_hidden_layers=None, hidden_size=None, davis=False, **cfg_over):
+    """Construct the reference `PSALM` (llava_phi.py:146; `davis`: PSALMForDAVISEval, :1477) on CPU, fp32, eval mode."""
     install()
-    from psalm.model.language_model.llava_phi import PSALM, LlavaConfig
+    from psalm.model.language_model.llava_phi import LlavaConfig
+    if davis:
+        from psalm.model.language_model.llava_phi import PSALMForDAVISEval as PSALM
+    else:
+        from psalm.model.language_model.llava_phi import PSALM
     kw = {}
     if num_hidden_layers is not None:
         kw["num_hidden_layers"] = num_hidden_layers

@@ -20,11 +20,11 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, model_ar
                           load_4bit=False, device_map="auto", device="cuda", torch_dtype=torch.float16, use_cuda_graph=False):
     if load_8bit or load_4bit:
         raise NotImplementedError("psalm_b200 runs 16-bit / fp32 storage; 8-bit / 4-bit loading (bitsandbytes) is not provided")
-    from .psalm import PSALM
+    from .psalm import PSALM, PSALMForDAVISEval
+    model_map = {"psalm": PSALM, "psalm_video": PSALMForDAVISEval}      # builder.py:45-48
     map_name = getattr(model_args, "model_map_name", "psalm")
-    if map_name != "psalm":
-        raise NotImplementedError("model_map_name %r: only 'psalm' (PSALM.eval_seg) is built; the DAVIS video model is "
-                                  "outside this build's scope" % map_name)
+    if map_name not in model_map:
+        raise KeyError("model_map_name %r: expected one of %s" % (map_name, sorted(model_map)))
     seg_task = getattr(model_args, "seg_task", "instance")          # builder.py:50
     tokenizer = None
     try:
@@ -33,7 +33,7 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, model_ar
     except Exception as e:   # no tokenizer files / no transformers: the segmentation path takes token ids
         tokenizer = None
         _ = e
-    model = PSALM.from_pretrained(model_path, torch_dtype=torch_dtype, device=device, seg_task=seg_task,
+    model = model_map[map_name].from_pretrained(model_path, torch_dtype=torch_dtype, device=device, seg_task=seg_task,
                                   use_cuda_graph=use_cuda_graph)
     image_processor = model.get_vision_tower().image_processor
     cfgj = os.path.join(model_path, "config.json")

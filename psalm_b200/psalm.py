@@ -262,7 +262,13 @@ class PSALM:
         h5, w5 = sizes[3]
         res5 = toks[3].view(toks[3].shape[0], h5, w5, -1).permute(0, 3, 1, 2)
         img_tok = self.model.mm_projector(res5)                                        # [B,n_img,hidden]
-        region_feat = self._region_features(img_tok, plan) if plan.region_pos is not None else None
+        region_feat = None
+        if plan.region_pos is not None:
+            src_tok = img_tok
+            if plan.vp_images is not None:   # DAVIS variant: pooled from the visual-prompt frame's map (llava_phi.py:1665-1670)
+                vtoks, vsizes = self.model.vision_tower.forward_tokens(plan.vp_images)
+                src_tok = self.model.mm_projector(vtoks[3].view(vtoks[3].shape[0], vsizes[3][0], vsizes[3][1], -1).permute(0, 3, 1, 2))
+            region_feat = self._region_features(src_tok, plan)
         embeds = SEQ.materialize_embeds(plan, self.model.embed_tokens, img_tok, self.seg_query, region_feat)
         hidden = self.model.phi(embeds, plan.attention_mask if plan.any_padding else None)
         seg_q = F.linear(SEQ.gather_seg_query(plan, hidden), *self.proj["seg_query_projector"])
@@ -429,11 +435,11 @@ class PSALM:
     def eval_seg(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
                  use_cache=None, output_attentions=None, output_hidden_states=None, images=None, return_dict=None,
                  seg_info=None, class_name_ids=None, class_name_embedding_indices=None, cls_indices=None,
-                 token_refer_id=None, refer_embedding_indices=None, is_thing_list=None, region_points=None):
+                 token_refer_id=None, refer_embedding_indices=None, is_thing_list=None, region_points=None, vp_images=None):
         if self.panoptic_on:
             assert is_thing_list is not None, "is_thing_list need to be given"   # llava_phi.py:1337-1339
             self.is_thing_list = is_thing_list
-        return self.eval_seg_async(region_points=region_points, input_ids=input_ids, attention_mask=attention_mask, images=images, seg_info=seg_info,
+        return self.eval_seg_async(region_points=region_points, vp_images=vp_images, input_ids=input_ids, attention_mask=attention_mask, images=images, seg_info=seg_info,
                                    class_name_ids=class_name_ids, class_name_embedding_indices=class_name_embedding_indices,
                                    cls_indices=cls_indices, token_refer_id=token_refer_id,
                                    refer_embedding_indices=refer_embedding_indices, is_thing_list=is_thing_list).result()
@@ -441,7 +447,7 @@ class PSALM:
     @torch.no_grad()
     def eval_seg_async(self, input_ids=None, attention_mask=None, images=None, seg_info=None, class_name_ids=None,
                        class_name_embedding_indices=None, cls_indices=None, token_refer_id=None,
-                       refer_embedding_indices=None, is_thing_list=None, lane=0, region_points=None):
+                       refer_embedding_indices=None, is_thing_list=None, lane=0, region_points=None, vp_images=None):
         """Submit one `eval_seg` call and return a `PendingSeg`; `.result()` gives what `eval_seg` returns.  `lane`
         selects an independent CUDA graph + static output buffers, so that a caller alternating lanes 0 / 1 can finish
         batch k (host merge, read-back) while the device already runs batch k+1.  `region_points`: optional per-sample
@@ -463,10 +469,12 @@ class PSALM:
         if has_regions:   # llava_phi.py:1346-1349: the regions come with the request (seg_info[i]['instances'].region_masks)
             import copy
             from .region import region_inputs
-            pts, img, counts = region_inputs(seg_info, region_points)
+            pts, img, counts = region_inputs(seg_info, region_points, "region_masks" if vp_images is None else "vp_region_masks")
             assert counts == plan.region_counts, "the munber of <region> tokens and regions needs to be same"   # llava_phi.py:593
             plan = copy.copy(plan)
             plan.region_points, plan.region_image = pts.to(self.device), img.to(self.device)
+            if vp_images is not None:
+                plan.vp_images = vp_images.to(self.device)
         fused, boxes = self._fused_applies(images.shape[-2:], seg_info)
         if self.use_cuda_graph and not has_regions:   # the number of regions varies per request: eager launches
             out = self.forward_core_graphed(images_d, plan, lane=lane, fuse_post=fused)
@@ -597,3 +605,17 @@ class PSALM:
                 r["gt"] = PP.sem_seg_postprocess(gt.to(mp.device).float(), (oh, ow), height, width)
             results.append(r)
         return results
+
+
+class PSALMForDAVISEval(PSALM):
+    """Video-object-segmentation variant (llava_phi.py:1477-2012, builder.py:47 'psalm_video'): the <region> prompts of
+    the current frame are pooled from a VISUAL-PROMPT frame (`vp_images`, usually the first frame of the clip) with
+    `seg_info[i]['instances'].vp_region_masks`; everything after the sequence splice is PSALM.eval_seg.  The reference's
+    `eval_seg` and `eval_video` of this class run the same computation."""
+
+    def eval_seg(self, *args, vp_images=None, **kw):
+        if vp_images is None:
+            raise ValueError("PSALMForDAVISEval needs vp_images (the visual-prompt frames, llava_phi.py:1497)")
+        return super().eval_seg(*args, vp_images=vp_images, **kw)
+
+    eval_video = eval_seg

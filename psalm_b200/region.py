@@ -32,12 +32,13 @@ def sample_region_points(region_masks, num_sample_point=NUM_SAMPLE_POINT):
     return torch.stack(out).float()
 
 
-def region_inputs(seg_info, region_points=None):
-    """seg_info: list of dicts with 'instances' (`.region_masks.tensor` [K,H,W], llava_phi.py:792) -> (points [R,P,2] fp32,
-    region_image [R] int32, counts).  `region_points`: optional per-sample list of pre-drawn points."""
+def region_inputs(seg_info, region_points=None, attr="region_masks"):
+    """seg_info: list of dicts with 'instances' (`.region_masks.tensor` [K,H,W], llava_phi.py:792; the DAVIS variant reads
+    `.vp_region_masks`, :1664) -> (points [R,P,2] fp32, region_image [R] int32, counts).  `region_points`: optional
+    per-sample list of pre-drawn points."""
     pts, img, counts = [], [], []
     for b, info in enumerate(seg_info):
-        p = region_points[b] if region_points is not None else sample_region_points(info["instances"].region_masks.tensor)
+        p = region_points[b] if region_points is not None else sample_region_points(getattr(info["instances"], attr).tensor)
         pts.append(p.float().cpu())
         img += [b] * p.shape[0]
         counts.append(int(p.shape[0]))

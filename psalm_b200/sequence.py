@@ -41,13 +41,14 @@ class SequencePlan:
     region_counts: Optional[tuple] = None        # regions per sample
     region_points: Optional[torch.Tensor] = None  # [R,P,2] fp32 sample points (y, x) in [0,1], set by the caller
     region_image: Optional[torch.Tensor] = None   # [R] int32 image index of every region
+    vp_images: Optional[torch.Tensor] = None      # [B,3,H,W] visual-prompt frames the regions are pooled from (DAVIS variant)
 
     def to(self, device):
         mv = lambda t: None if t is None else t.to(device, non_blocking=True)  # noqa: E731
         return SequencePlan(self.B, self.T, mv(self.tok_ids), mv(self.img_pos), mv(self.seg_pos), mv(self.pad_pos),
                             mv(self.attention_mask), self.any_padding, mv(self.cls_pool), mv(self.refer_pool),
                             self.n_img, self.n_q, mv(self.region_pos), self.region_counts, mv(self.region_points),
-                            mv(self.region_image))
+                            mv(self.region_image), mv(self.vp_images))
 
 
 def build_plan(input_ids, attention_mask, n_img, n_q, class_name_ids=None, cls_indices=None,

@@ -89,7 +89,7 @@ def synth_state_dict(cfg: PsalmConfig = PsalmConfig(), seed=0, include_lm_head=F
 
 
 def synth_inputs(batch=1, height=1024, width=1024, task="panoptic", n_classes=134, seed=1, text_len=(12, 8, 9),
-                 refer_len=12, vocab_hi=50000, ragged=False, n_regions=3):
+                 refer_len=12, vocab_hi=50000, ragged=False, n_regions=3, visual_prompt_frame=False):
     """Synthetic request in the reference's input contract.
 
     panoptic / instance / semantic: 12 text ids + <image> + 8 ids + n_classes x (<cls>, one id) + 9 ids +
@@ -171,9 +171,14 @@ def synth_inputs(batch=1, height=1024, width=1024, task="panoptic", n_classes=13
                 x0 = int(torch.randint(0, width - ww + 1, (1,), generator=g))
                 rm[j, y0:y0 + hh, x0:x0 + ww] = True
             inst = Instances((height, width))
-            inst.region_masks = BitMasks(rm)
+            if visual_prompt_frame:   # DAVIS variant: the masks live on the visual-prompt frame (llava_phi.py:1664)
+                inst.vp_region_masks = BitMasks(rm)
+            else:
+                inst.region_masks = BitMasks(rm)
             inst.gt_masks = rm.float()
             out["seg_info"][b]["instances"] = inst
+        if visual_prompt_frame:
+            out["vp_images"] = torch.randn(batch, 3, height, width, generator=g)
     if task == "panoptic":
         out["is_thing_list"] = [True] * min(80, n_classes - 1) + [False] * max(0, n_classes - 1 - 80)
     return out

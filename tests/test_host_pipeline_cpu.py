@@ -156,3 +156,31 @@ def test_region_host_pipeline_matches_reference_golden(monkeypatch, golden):
     assert np.abs(area - g["region_mask_area"]).max() <= 2          # |logit| ~ 0 ties only
     gt = res[0]["gt"].reshape(-1)[torch.from_numpy(g["region_gt_idx"])].numpy()
     assert np.allclose(gt, g["region_gt"], atol=1e-6)
+
+
+def test_davis_variant_matches_reference_golden(monkeypatch, golden):
+    """PSALMForDAVISEval: region features pooled from the visual-prompt frame (`vp_images`, `vp_region_masks`), against
+    the fixture produced by the UNMODIFIED reference class (oracle/gen_golden_modules.py, case davis_192x192)."""
+    from psalm_b200.psalm import PSALMForDAVISEval
+    H = W = 192
+    sd = synth.synth_state_dict(SMALL, seed=13)
+    inp = synth.synth_inputs(batch=1, height=H, width=W, task="region", seed=14, visual_prompt_frame=True)
+    emu.install(monkeypatch)
+
+    class _Emu(PSALMForDAVISEval):
+        @staticmethod
+        def _check_runtime(device):
+            pass
+    m = _Emu(sd, SMALL, torch.float32, "cpu", "region")
+    g = golden("e2e_davis_192x192_b1.npz")
+    from psalm_b200.region import region_inputs
+    plan = m.make_plan(inp["input_ids"], inp["attention_mask"], (H, W))       # (eval_video itself needs CUDA streams)
+    plan.region_points, plan.region_image, _ = region_inputs(inp["seg_info"], [torch.from_numpy(g["region_points_0"])],
+                                                             "vp_region_masks")
+    plan.vp_images = inp["vp_images"]
+    res = m.post_process(m.forward_core(inp["images"], plan), (H, W), inp["seg_info"])
+    inst = res[0]["instances"]
+    assert np.allclose(inst.scores.numpy(), g["region_scores"], rtol=2e-3, atol=2e-4)
+    assert np.abs(inst.pred_masks.flatten(1).sum(1).numpy() - g["region_mask_area"]).max() <= 2
+    with pytest.raises(ValueError, match="vp_images"):
+        m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"], seg_info=inp["seg_info"])

@@ -89,3 +89,47 @@ def test_region_prompt_errors():
     with pytest.raises(AssertionError, match="munber of <region> tokens"):   # the reference's message (llava_phi.py:593)
         m.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
                    seg_info=inp["seg_info"], region_points=wrong)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 2.5e-1)], ids=["f32", "bf16"])
+def test_davis_variant_eval_video(golden, dtype, tol):
+    """PSALMForDAVISEval.eval_video on the GPU against the reference-generated fixture (regions pooled from the
+    visual-prompt frame)."""
+    from psalm_b200.psalm import PSALMForDAVISEval
+    H = W = 192
+    sd = synth.synth_state_dict(SMALL, seed=13)
+    inp = synth.synth_inputs(batch=1, height=H, width=W, task="region", seed=14, visual_prompt_frame=True)
+    g = golden("e2e_davis_192x192_b1.npz")
+    m = PSALMForDAVISEval(sd, SMALL, dtype, "cuda", "region")
+    res = m.eval_video(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                       seg_info=inp["seg_info"], vp_images=inp["vp_images"],
+                       region_points=[torch.from_numpy(g["region_points_0"])])
+    sc = res[0]["instances"].scores.float().cpu().numpy()
+    ref = g["region_scores"]
+    assert sc.shape == ref.shape
+    err = np.linalg.norm(sc - ref) / np.linalg.norm(ref)
+    print("davis %s: region-score l2-rel %.3e" % (dtype, err))
+    if dtype != torch.float32:
+        # 16-bit storage: the scores multiply a sigmoid by a thresholded-mask statistic of a random-weight model, so the
+        # end-to-end number is loose (asserted < 0.6); what this variant adds - the region features pooled from the
+        # visual-prompt frame - is asserted tightly against the oracle's
+        from oracle import psalm_oracle as O
+        from psalm_b200.region import region_inputs
+        pts = [torch.from_numpy(g["region_points_0"])]
+        with torch.no_grad():
+            _, it = O.eval_seg(sd, inp["input_ids"], inp["attention_mask"], inp["images"], inp["seg_info"], task="region",
+                               phi_cfg=SMALL_O, return_intermediates=True, vp_images=inp["vp_images"], region_points=pts)
+        plan = m.make_plan(inp["input_ids"], inp["attention_mask"], (H, W))
+        plan.region_points, plan.region_image, _ = region_inputs(inp["seg_info"], pts, "vp_region_masks")
+        plan.vp_images = inp["vp_images"]
+        tr = {}
+        m.forward_core(inp["images"].cuda(), plan.to("cuda"), trace=tr)
+        want = torch.cat(it["region_features"], 0).squeeze(1)
+        got = tr["region_features"].float().cpu()
+        assert (got - want).norm() / want.norm() < 3e-2
+        assert err < 0.6
+        return
+    assert err < tol
+    if dtype == torch.float32:
+        assert np.allclose(sc, ref, rtol=1e-3, atol=1e-4)
+        assert np.abs(res[0]["instances"].pred_masks.flatten(1).sum(1).cpu().numpy() - g["region_mask_area"]).max() <= 2

@@ -92,8 +92,18 @@ def test_from_pretrained_and_load_pretrained_model(monkeypatch, tmp_path):
         save_file({k: v.contiguous() for k, v in bad.items()}, str(d2 / "model.safetensors"))
         json.dump(json.load(open(d / "config.json")), open(d2 / "config.json", "w"))
         builder.from_pretrained(cls, str(d2), torch_dtype=torch.float32, device="cpu")
-    with pytest.raises(NotImplementedError):
-        builder.load_pretrained_model(str(d), None, "psalm", types.SimpleNamespace(model_map_name="psalm_video"), device="cpu")
+    with pytest.raises(KeyError, match="model_map_name"):     # builder.py:45-49: 'psalm' or 'psalm_video'
+        builder.load_pretrained_model(str(d), None, "psalm", types.SimpleNamespace(model_map_name="psalm_audio"), device="cpu")
+    from psalm_b200.psalm import PSALMForDAVISEval
+
+    class _EmuVideo(PSALMForDAVISEval):
+        @staticmethod
+        def _check_runtime(device):
+            pass
+    monkeypatch.setattr("psalm_b200.psalm.PSALMForDAVISEval", _EmuVideo)
+    args = types.SimpleNamespace(model_map_name="psalm_video", seg_task="region")
+    _, vmodel, _, _ = builder.load_pretrained_model(str(d), None, "psalm", args, torch_dtype=torch.float32, device="cpu")
+    assert isinstance(vmodel, PSALMForDAVISEval) and vmodel.region_on and vmodel.eval_video.__func__ is vmodel.eval_seg.__func__
 
 
 def test_prepare_inputs_labels_for_multimodal_matches_the_oracle(monkeypatch):
