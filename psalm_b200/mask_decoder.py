@@ -14,6 +14,8 @@ Mirrors `MultiScaleMaskedTransformerDecoderForOPTPreTrain.forward_woconcat`
     nine are thresholded and thrown away (236 MB of logits per image in the reference);
   * `(sigmoid(x) < 0.5)` is `x < 0`; fully blocked rows are opened by a per-row flag (:647).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -143,13 +145,37 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             k_all = [torch.addmm(posk[li], ms_tokens[li].reshape(-1, Hd), w["xk_all%d.w" % li].t()).view(B, -1, 3 * Hd)
                      for li in range(3)]
             v_all = [F.linear(ms_tokens[li], w["xv_all%d.w" % li], vb[li]) for li in range(3)]
+        qc = None
+        fold_q = fused_kv and not os.environ.get("PSALM_NO_QCONST")
+        if fold_q:
+            # (output + query_pos) W^T + b = output W^T + (query_pos W^T + b): the position terms of the cross-attention
+            # query and of the self-attention query / key do not depend on the input; they enter the GEMMs as the additive
+            # C matrix (no `output + query_pos` passes), and the self-attention K and V projections share one GEMM whose
+            # halves the attention kernel reads as row-strided views.  Never evicted: CUDA graphs hold these pointers.
+            if not hasattr(self, "_q_const"):
+                self._q_const = {}
+            qc = self._q_const.get(B)
+            if qc is None:
+                qp = self.query_embed.float()
+                qc = []
+                for i in range(cfg.dec_layers):
+                    lin = lambda n: qp @ w[n + ".w"].float().t() + w[n + ".b"].float()   # noqa: E731
+                    cx = lin("x%d.q" % i).to(self.dtype).repeat(B, 1).contiguous()
+                    cs = lin("s%d.q" % i).to(self.dtype).repeat(B, 1).contiguous()
+                    ckv = torch.cat([lin("s%d.k" % i), w["s%d.v.b" % i].float().expand(Q, -1)], 1)
+                    wkv = torch.cat([w["s%d.k.w" % i], w["s%d.v.w" % i]], 0).contiguous()
+                    qc.append((cx, cs, ckv.to(self.dtype).repeat(B, 1).contiguous(), wkv))
+                self._q_const[B] = qc
         bits, row_open = mask_for(0, output)
         for i in range(cfg.dec_layers):
             li = i % 3
             if hooks is not None:
                 output, bits, row_open = hooks.before_layer(i, output, bits, row_open, lambda o_, lv=li: mask_for(lv, o_))
             # masked cross-attention (:93-105): q = tgt + query_pos, k = memory + pos, v = memory
-            q = F.linear(output + qpos, w["x%d.q.w" % i], w["x%d.q.b" % i])
+            if fold_q:
+                q = torch.addmm(qc[i][0], output.reshape(-1, Hd), w["x%d.q.w" % i].t()).view(B, Q, Hd)
+            else:
+                q = F.linear(output + qpos, w["x%d.q.w" % i], w["x%d.q.b" % i])
             if fused_kv:
                 j = i // 3
                 k, v = k_all[li][:, :, j * Hd:(j + 1) * Hd], v_all[li][:, :, j * Hd:(j + 1) * Hd]
@@ -163,11 +189,17 @@ class MultiScaleMaskedTransformerDecoderForOPTPreTrain:
             output = kernels.add_layer_norm(output, w["x%d.n.w" % i], w["x%d.n.b" % i],
                                             r1=F.linear(a, w["x%d.o.w" % i], w["x%d.o.b" % i]))
             # query self-attention (:35-45): q = k = tgt + query_pos, v = tgt
-            xq = output + qpos
-            q = F.linear(xq, w["s%d.q.w" % i], w["s%d.q.b" % i])     # three contiguous outputs: no slicing copies
-            k = F.linear(xq, w["s%d.k.w" % i], w["s%d.k.b" % i])
-            v = F.linear(output, w["s%d.v.w" % i], w["s%d.v.b" % i])
-            a = kernels.cross_attention(q, k, v, None, None, nh, splits=1)
+            if fold_q:
+                o2 = output.reshape(-1, Hd)
+                q = torch.addmm(qc[i][1], o2, w["s%d.q.w" % i].t()).view(B, Q, Hd)
+                kv = torch.addmm(qc[i][2], o2, qc[i][3].t()).view(B, Q, 2 * Hd)
+                a = kernels.masked_cross_attention(q, kv[:, :, :Hd], kv[:, :, Hd:], None, None, nh)
+            else:
+                xq = output + qpos
+                q = F.linear(xq, w["s%d.q.w" % i], w["s%d.q.b" % i])     # three contiguous outputs: no slicing copies
+                k = F.linear(xq, w["s%d.k.w" % i], w["s%d.k.b" % i])
+                v = F.linear(output, w["s%d.v.w" % i], w["s%d.v.b" % i])
+                a = kernels.cross_attention(q, k, v, None, None, nh, splits=1)
             output = kernels.add_layer_norm(output, w["s%d.n.w" % i], w["s%d.n.b" % i],
                                             r1=F.linear(a, w["s%d.o.w" % i], w["s%d.o.b" % i]))
             # FFN (:158-162)

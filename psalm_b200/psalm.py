@@ -22,6 +22,8 @@ How it differs from the reference on purpose (results are unchanged, see DESIGN.
 import contextlib
 from collections import OrderedDict
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -309,15 +311,19 @@ class PSALM:
         from . import kernels
         thing = PP.thing_tensor(self.is_thing_list, self.device) if (self.panoptic_on and self.instance_on) else None
         pm = out["pred_masks"].view(B, Q, H4, W4)
-        res = []
+        sizes, crops = [], []
         for b in range(B):
             oh, ow, height, width = geoms[b] if geoms is not None else (Hp, Wp, Hp, Wp)
-            crop = None if (oh, ow, height, width) == (Hp, Wp, Hp, Wp) else (Hp, Wp, oh, ow)
-            res.append(PP.fused_device(kernels, pm[b], height, width, cls[b] if cls is not None else None,
-                                       out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None, thing,
-                                       self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
-                                       self.test_topk_per_image, self.object_mask_threshold, crop=crop))
-        return res
+            sizes.append((height, width))
+            crops.append(None if (oh, ow, height, width) == (Hp, Wp, Hp, Wp) else (Hp, Wp, oh, ow))
+        if os.environ.get("PSALM_NO_BATCH_POST"):
+            return [PP.fused_device(kernels, pm[b], sizes[b][0], sizes[b][1], cls[b] if cls is not None else None,
+                                    out["pred_SEG_logits"][b] if out["pred_SEG_logits"] is not None else None, thing,
+                                    self.semantic_on, self.instance_on, self.panoptic_on, self.referring_on,
+                                    self.test_topk_per_image, self.object_mask_threshold, crop=crops[b]) for b in range(B)]
+        return PP.fused_device_batch(kernels, pm, sizes, cls, out["pred_SEG_logits"], thing, self.semantic_on,
+                                     self.instance_on, self.panoptic_on, self.referring_on, self.test_topk_per_image,
+                                     self.object_mask_threshold, crops=crops)
 
     MAX_GRAPHS = 8   # each entry owns static buffers + a private pool (hundreds of MB at 1024^2, B = 4)
 

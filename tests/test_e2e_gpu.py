@@ -257,6 +257,12 @@ def test_mapper_flow_uses_the_fused_kernel_and_matches_the_oracle(monkeypatch):
         calls.append(k.get("crop"))
         return real(*a, **k)
     monkeypatch.setattr(PP, "fused_device", spy)
+    real_b = PP.fused_device_batch
+
+    def spy_b(*a, **k):        # the graph path batches the small algebra of all images
+        calls.extend(k.get("crops"))
+        return real_b(*a, **k)
+    monkeypatch.setattr(PP, "fused_device_batch", spy_b)
     outs = {}
     for graph in (False, True):
         m = PSALM(sd, SMALL, torch.bfloat16, "cuda", "panoptic", use_cuda_graph=graph)
