@@ -338,6 +338,8 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda._sleep(80_000_000)
         out = model.forward_core(images_d, plan_d)
         return model.post_process(out, (IMG, IMG), inp["seg_info"])
+    overlap_keep = model.overlap_branches
+    model.overlap_branches = False     # per-kernel rooflines: every kernel timed alone, not under the other branch
     step_eager()
     kernels.PROFILE_EVENTS = {}
     l0 = kernels.launches()
@@ -347,6 +349,7 @@ def run_ours(args, rank, world, local_rank):
     launches = kernels.launches() - l0
     ev = kernels.PROFILE_EVENTS
     kernels.PROFILE_EVENTS = None
+    model.overlap_branches = overlap_keep
     msda_us = [a.elapsed_time(b) * 1e3 for a, b in ev.get("msda", [])]
     esz_ = 4 if dtype == torch.float32 else 2
     T_seq = int(plan_d.T)
@@ -450,9 +453,20 @@ def run_ours(args, rank, world, local_rank):
                                      images=images_d, seg_info=inp["seg_info"], **kw)
         H4, W4 = out_timed["mask_size"]
         it0 = None
-        for b in range(min(args.acc_images, B)):
-            dt, ores, it = oracle_eval(sd, inp, b, threads, relaxed=True)
-            if b == 0:
+        n_acc = args.acc_images if args.acc_images > 0 else max(2, 16 // world)    # 16 images over the ranks by default
+        cur_inp, cur_res, cur_masks = inp, res_relaxed, out_timed["pred_masks"]
+        for n in range(n_acc):
+            b = n % B
+            if n > 0 and b == 0:   # a further batch of held images, through the timed graph path
+                fresh = bench_inputs(B, 1000 + 17 * rank + n)
+                cur_inp = dict(inp, images=fresh["images"], images_u8=fresh["images_u8"])      # same prompt, new images
+                cur_res = model.eval_seg(input_ids=cur_inp["input_ids"], attention_mask=cur_inp["attention_mask"],
+                                         images=cur_inp["images"].to(dev), seg_info=cur_inp["seg_info"], **kw)
+                cur_res = [dict(panoptic_seg=(r["panoptic_seg"][0].clone(), r["panoptic_seg"][1]), sem_arg=r["sem_seg"].argmax(0).cpu())
+                           for r in cur_res]
+                cur_masks = model.forward_core_graphed(cur_inp["images"].to(dev), plan_d)["pred_masks"].clone()
+            dt, ores, it = oracle_eval(sd, cur_inp, b, threads, relaxed=True)
+            if n == 0:
                 it0 = it
                 cpu_line = {"value": 100.0 / dt, "unit": "masks/s", "cores": threads, "kind": "port",
                             "sample": "one 1024^2 panoptic image, fp32, single pass, no warm-up"}
@@ -467,11 +481,12 @@ def run_ours(args, rank, world, local_rank):
                                        "stage / decoder layer fed the oracle's inputs; sensitivity = the ORACLE's decoder "
                                        "re-run on its own inputs rounded to bf16 (the masked attention thresholds mask "
                                        "logits: a discontinuity of the reference itself)"}
-            r, o = res_relaxed[b], ores[0]
+            r, o = cur_res[b], ores[0]
             acc.add_panoptic(r["panoptic_seg"][0].cpu().numpy(), r["panoptic_seg"][1], o["panoptic_seg"][0].numpy(),
                              o["panoptic_seg"][1])
-            acc.add_semantic(r["sem_seg"].argmax(0).cpu().numpy(), o["sem_seg"].argmax(0).numpy())
-            up = torch.nn.functional.interpolate(out_timed["pred_masks"][b].float().view(1, -1, H4, W4), size=(IMG, IMG),
+            sem_arg = r["sem_arg"] if "sem_arg" in r else r["sem_seg"].argmax(0).cpu()
+            acc.add_semantic(sem_arg.numpy(), o["sem_seg"].argmax(0).numpy())
+            up = torch.nn.functional.interpolate(cur_masks[b].float().view(1, -1, H4, W4), size=(IMG, IMG),
                                                  mode="bilinear", align_corners=False)[0]
             acc.add_masks((up > 0).cpu(), it["mask_pred"][0] > 0)
             acc.add_image()
@@ -548,7 +563,8 @@ def main():
     ap.add_argument("--no-oracle", action="store_true", help="skip the CPU-oracle legs (cpu_baseline, parity, accuracy)")
     ap.add_argument("--no-fp32-parity", action="store_true", help="skip the fp32-storage parity pass (N = 1)")
     ap.add_argument("--no-batch1", action="store_true", help="skip the single-image latency measurement")
-    ap.add_argument("--acc-images", type=int, default=2, help="held images per rank scored against the oracle")
+    ap.add_argument("--acc-images", type=int, default=0,
+                    help="held images per rank scored against the oracle (0 = 16 images divided over the ranks, at least 2)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -95,6 +95,7 @@ class PSALM:
         self.use_cuda_graph = use_cuda_graph
         # one fused kernel for the task heads (16-bit storage); fp32 parity runs keep the exact torch path
         self._fused_postprocess = dtype != torch.float32
+        self.overlap_branches = not os.environ.get("PSALM_NO_OVERLAP")   # pixel decoder || LLM prefill on two streams
         self.cfg, self.dtype, self.device = cfg, dtype, torch.device(device)
         sd = state_dict
         cv = lambda t: t.to(device=device, dtype=dtype).contiguous()  # noqa: E731
@@ -264,6 +265,19 @@ class PSALM:
         h5, w5 = sizes[3]
         res5 = toks[3].view(toks[3].shape[0], h5, w5, -1).permute(0, 3, 1, 2)
         img_tok = self.model.mm_projector(res5)                                        # [B,n_img,hidden]
+        # The pixel decoder needs only the Swin maps, the LLM only the projector tokens: the two branches run on two
+        # streams (also inside a captured graph) and meet at the mask decoder.  The LLM branch is a chain of library GEMMs
+        # at the tensor-core peak whose last waves leave SMs idle; the pixel decoder's memory-bound kernels fill them.
+        branch, main = None, None
+        if self.overlap_branches and toks[0].is_cuda:
+            main = torch.cuda.current_stream(self.device)
+            if not hasattr(self, "_branch_stream"):
+                self._branch_stream = torch.cuda.Stream(device=self.device, priority=-1 if os.environ.get("PSALM_BRANCH_PRIO") else 0)
+            self._branch_stream.wait_stream(main)
+            with torch.cuda.stream(self._branch_stream):
+                branch = self.pixel_decoder.forward_tokens(toks, sizes)
+            for t in toks:
+                t.record_stream(self._branch_stream)
         region_feat = None
         if plan.region_pos is not None:
             src_tok = img_tok
@@ -285,7 +299,13 @@ class PSALM:
                 raise KeyError("region prompts need region_projector.* in the checkpoint")
             rows = F.linear(SEQ.gather_region_rows(plan, hidden), *self.proj["region_projector"])
             region_emb = list(torch.split(rows, list(plan.region_counts), 0))
-        mask_features, ms, ms_sizes = self.pixel_decoder.forward_tokens(toks, sizes)
+        if branch is None:
+            mask_features, ms, ms_sizes = self.pixel_decoder.forward_tokens(toks, sizes)
+        else:   # join the pixel-decoder branch
+            mask_features, ms, ms_sizes = branch
+            main.wait_stream(self._branch_stream)
+            for t in [mask_features] + list(ms):
+                t.record_stream(main)
         out = self.predictor.forward_tokens(ms, ms_sizes, mask_features, sizes[0], seg_q, SEG_emb, cls_emb,
                                             region_embedding_list=region_emb)
         out["mask_size"] = sizes[0]
