@@ -269,7 +269,8 @@ class PSALM:
         # streams (also inside a captured graph) and meet at the mask decoder.  The LLM branch is a chain of library GEMMs
         # at the tensor-core peak whose last waves leave SMs idle; the pixel decoder's memory-bound kernels fill them.
         branch, main = None, None
-        if self.overlap_branches and toks[0].is_cuda:
+        if self.overlap_branches and toks[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            # (graph capture only: eager launches are host bound, two streams would buy nothing there)
             main = torch.cuda.current_stream(self.device)
             if not hasattr(self, "_branch_stream"):
                 self._branch_stream = torch.cuda.Stream(device=self.device, priority=-1 if os.environ.get("PSALM_BRANCH_PRIO") else 0)
