@@ -127,6 +127,30 @@ def test_cuda_graph_replay_matches_eager():
         assert torch.allclose(a[0]["instances"].scores, b[0]["instances"].scores, rtol=1e-5, atol=1e-7)
 
 
+def test_cuda_graphs_of_different_sizes_and_batches_alternate():
+    """Graphs captured for several (image size, batch) keys hold device pointers of per-size cached tensors (position
+    terms of the pixel decoder, K / V constants of the mask decoder): replaying A, B, C, A must keep matching eager
+    launches - a cache that dropped size A's tensors when B arrived would feed the first graph freed memory."""
+    from psalm_b200.psalm import PSALM
+    sd = synth.synth_state_dict(SMALL, seed=0)
+    eager = PSALM(sd, SMALL, torch.bfloat16, "cuda", "panoptic", use_cuda_graph=False)
+    graphed = PSALM(sd, SMALL, torch.bfloat16, "cuda", "panoptic", use_cuda_graph=True)
+    keys = {"A": (1, 192, 192), "B": (2, 160, 224), "C": (1, 256, 128)}
+    for step, name in enumerate("ABCABA"):
+        batch, H, W = keys[name]
+        inp = synth.synth_inputs(batch=batch, height=H, width=W, task="panoptic", n_classes=12, seed=10 + step)
+        kw = {k: inp[k] for k in ("class_name_ids", "cls_indices", "class_name_embedding_indices", "is_thing_list")}
+        a = eager.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                           seg_info=inp["seg_info"], **kw)
+        b = graphed.eval_seg(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], images=inp["images"],
+                             seg_info=inp["seg_info"], **kw)
+        torch.cuda.synchronize()
+        for i in range(batch):
+            assert torch.equal(a[i]["panoptic_seg"][0], b[i]["panoptic_seg"][0]), (step, name, i)
+            assert torch.equal(a[i]["sem_seg"], b[i]["sem_seg"]), (step, name, i)
+    assert 3 <= len(graphed._graphs) <= 6        # one graph per (size, batch, prompt length) key; none evicted
+
+
 def _oracle(sd, inp, task):
     from oracle import psalm_oracle as O
     phi = dict(hidden=256, layers=2, heads=4, inter=1024, eps=1e-5, theta=10000.0, rotary_frac=0.5)
