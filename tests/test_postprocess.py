@@ -69,6 +69,28 @@ def test_fused_glue_cpu(monkeypatch, task):
     _compare(ref, got, task, 2e-3)
 
 
+@pytest.mark.parametrize("task", ["panoptic", "instance", "semantic", "referring"])
+def test_batched_glue_cpu(monkeypatch, task):
+    """fused_device_batch (the small algebra of all images of a step in one set of launches) gives, image by image,
+    what the step-by-step reference path gives - three images with different logits / class scores."""
+    from psalm_b200 import kernels
+    monkeypatch.setattr(kernels, "postproc_fused", emu.postproc_fused)
+    H, W = 96, 160
+    per = [_inputs(10 + b) for b in range(3)]
+    thing = per[0][3]
+    logits = torch.stack([p[0] for p in per])
+    cls = None if task == "referring" else torch.stack([p[1] for p in per])
+    seg = torch.stack([p[2] for p in per]) if task == "referring" else None
+    ds = PP.fused_device_batch(kernels, logits, [(H, W)] * 3, cls, seg, PP.thing_tensor(thing, "cpu") if task == "panoptic" else None,
+                               task in ("semantic", "panoptic"), task in ("instance", "panoptic"), task == "panoptic",
+                               task == "referring", 100, 0.8)
+    assert len(ds) == 3
+    for b in range(3):
+        got = PP.fused_host(ds[b], thing, 0.8)
+        ref = _reference_path(per[b][0], per[b][1], per[b][2], thing, H, W, task)
+        _compare(ref, got, task, 2e-3)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("task", ["panoptic", "instance", "semantic", "referring"])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
