@@ -10,7 +10,9 @@ semantics: new size = round-half-up of the scaled size, PIL bilinear resampling 
 bottom / right.  Ground-truth handling (panoptic PNGs, polygons) belongs to training / evaluation and is not restated.
 
 On top of the reference contract, `preprocess` also returns `image_u8` (the padded uint8 CHW image): `PSALM.eval_seg`
-accepts it directly and normalises on the device (csrc/preproc.cu), a 4x smaller upload."""
+accepts it directly and normalises on the device (csrc/preproc.cu), a 4x smaller upload.  `preprocess_device` moves the
+resize and the padding to the device too, with Pillow's 8-bit resampling arithmetic restated exactly (`pil_bilinear_resize`:
+bit-identical to `Image.resize(BILINEAR)`, tests/test_surface_cpu.py)."""
 import numpy as np
 import torch
 
@@ -30,6 +32,51 @@ def resize_shortest_edge_shape(h, w, short, max_size):
         scale = max_size * 1.0 / max(newh, neww)
         newh, neww = newh * scale, neww * scale
     return int(newh + 0.5), int(neww + 0.5)
+
+
+_PRECISION_BITS = 32 - 8 - 2      # Pillow: src/libImaging/Resample.c, 8 bits per channel
+_COEFFS = {}
+
+
+def _pil_bilinear_coeffs(in_size, out_size, device):
+    """Dense [out_size, in_size] matrix of the INTEGER coefficients Pillow's 8-bit resampler uses for the BILINEAR filter
+    over the whole image (Resample.c: precompute_coeffs + normalize_coeffs_8bpc): triangle filter of support
+    max(scale, 1) around the source centre (xx + 0.5) * scale, normalised in double, scaled by 2^22 and rounded half away
+    from zero.  Cached per (sizes, device)."""
+    key = (in_size, out_size, str(device))
+    if key not in _COEFFS:
+        scale = in_size / out_size
+        filterscale = max(scale, 1.0)
+        support = 1.0 * filterscale
+        K = np.zeros((out_size, in_size), dtype=np.float64)
+        for xx in range(out_size):
+            center = (xx + 0.5) * scale
+            xmin = max(int(center - support + 0.5), 0)
+            xmax = min(int(center + support + 0.5), in_size)
+            arg = (np.arange(xmax - xmin) + xmin - center + 0.5) / filterscale
+            w = np.where(np.abs(arg) < 1.0, 1.0 - np.abs(arg), 0.0)
+            ww = w.sum()
+            K[xx, xmin:xmax] = w / ww if ww != 0.0 else w
+        K = np.trunc(0.5 + K * (1 << _PRECISION_BITS))      # all bilinear coefficients are >= 0
+        _COEFFS[key] = torch.from_numpy(K).to(device)
+    return _COEFFS[key]
+
+
+def pil_bilinear_resize(image_hwc_u8, out_h, out_w):
+    """uint8 [H,W,C] tensor (any device) -> uint8 [out_h,out_w,C] with the bits of
+    `PIL.Image.resize((out_w, out_h), Image.BILINEAR)`: Pillow's two passes (horizontal, then vertical, uint8 in between),
+    each `clip8((sum_x pixel * coeff + 2^21) >> 22)`.  The sums are integers below 2^34, so float64 GEMMs evaluate them
+    exactly in any summation order - on the GPU this is two small DGEMMs instead of a host-side resize of every image."""
+    x = image_hwc_u8.double()
+    H, W, _ = x.shape
+    half, one = float(1 << (_PRECISION_BITS - 1)), float(1 << _PRECISION_BITS)
+    if W != out_w:
+        x = torch.einsum("hwc,ow->hoc", x, _pil_bilinear_coeffs(W, out_w, x.device))
+        x = torch.floor((x + half) / one).clamp_(0, 255)
+    if H != out_h:
+        x = torch.einsum("hwc,oh->owc", x, _pil_bilinear_coeffs(H, out_h, x.device))
+        x = torch.floor((x + half) / one).clamp_(0, 255)
+    return x.to(torch.uint8)
 
 
 class SegImageProcessor:
@@ -66,6 +113,32 @@ class SegImageProcessor:
         d["image_u8"] = u8
         d["image"] = (u8 - self.pixel_mean) / self.pixel_std
         d["padding_mask"] = torch.as_tensor(padding_mask)
+        d["transforms"] = None
+        return d
+
+
+    def preprocess_device(self, dataset_dict, device="cuda"):
+        """`preprocess` with the resize, the padding and (inside `PSALM.eval_seg`, csrc/preproc.cu) the normalisation on
+        the DEVICE: the decoded image is uploaded as it is (H x W x 3 bytes, usually far fewer than the padded
+        1024^2 x 3), resized with Pillow's exact 8-bit arithmetic (`pil_bilinear_resize`), padded with 128 at the bottom /
+        right.  Returns the same dict as `preprocess` without the float `image`; `image_u8` [3,S,S] lives on `device`
+        and is bit-identical to the host path's."""
+        d = dict(dataset_dict)
+        image = self._read(d)
+        h, w = image.shape[:2]
+        d.setdefault("height", h)
+        d.setdefault("width", w)
+        S = self.image_size
+        nh, nw = resize_shortest_edge_shape(h, w, S, S)
+        x = torch.as_tensor(np.ascontiguousarray(image)).to(device, non_blocking=True)
+        if (nh, nw) != (h, w):
+            x = pil_bilinear_resize(x, nh, nw)
+        padded = torch.full((3, S, S), int(self.pad_value), dtype=torch.uint8, device=device)
+        padded[:, :nh, :nw] = x[:S, :S].permute(2, 0, 1)
+        padding_mask = torch.ones((S, S), dtype=torch.bool)
+        padding_mask[:nh, :nw] = False
+        d["image_u8"] = padded
+        d["padding_mask"] = padding_mask
         d["transforms"] = None
         return d
 

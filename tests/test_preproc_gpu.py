@@ -54,3 +54,17 @@ def test_uint8_staged_eval_equals_float_contract():
             torch.cuda.synchronize()
             for x, r in zip(sem_a, b):
                 assert torch.equal(x, r["sem_seg"])
+
+
+def test_device_side_resize_equals_the_host_path():
+    """SegImageProcessor.preprocess_device on the GPU: the float64 GEMMs evaluate Pillow's integer sums exactly, so the
+    padded uint8 image equals the host (PIL) path bit for bit."""
+    import numpy as np
+    from psalm_b200.image_processor import SegImageProcessor
+    proc = SegImageProcessor(1024, "panoptic")
+    for h, w in ((480, 640), (1333, 800), (300, 1100)):
+        img = (np.random.RandomState(h + w).rand(h, w, 3) * 255).astype(np.uint8)
+        a = proc.preprocess({"image_array": img})
+        b = proc.preprocess_device({"image_array": img}, device="cuda")
+        assert b["image_u8"].is_cuda and torch.equal(a["image_u8"], b["image_u8"].cpu())
+        assert torch.equal(a["padding_mask"], b["padding_mask"])

@@ -128,3 +128,25 @@ def test_prepare_inputs_labels_for_multimodal_matches_the_oracle(monkeypatch):
     m.initialize_vision_tokenizer(types.SimpleNamespace(mm_use_im_patch_token=False, mm_use_im_start_end=False), None)
     with pytest.raises(NotImplementedError):
         m.initialize_vision_tokenizer(types.SimpleNamespace(mm_use_im_patch_token=True, mm_use_im_start_end=False), None)
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (480, 640), (427, 640), (1200, 1600), (333, 500), (900, 600), (1024, 1024), (100, 37)])
+def test_device_side_resize_has_pillow_bits(shape):
+    """image_processor.pil_bilinear_resize restates Pillow's 8-bit BILINEAR resampler exactly (integer coefficients scaled
+    by 2^22, horizontal pass then vertical pass with uint8 in between): bit-identical to Image.resize for up- and
+    down-scaling, and preprocess_device == preprocess on `image_u8` / `padding_mask` (torch ops only: the same arithmetic
+    runs on the GPU, checked against the CPU result in tests/test_preproc_gpu.py)."""
+    import numpy as np
+    from PIL import Image
+    from psalm_b200.image_processor import SegImageProcessor, pil_bilinear_resize, resize_shortest_edge_shape
+    h, w = shape
+    img = (np.random.RandomState(h * 7 + w).rand(h, w, 3) * 255).astype(np.uint8)
+    nh, nw = resize_shortest_edge_shape(h, w, 1024, 1024)
+    ref = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BILINEAR))
+    got = pil_bilinear_resize(torch.from_numpy(img), nh, nw).numpy()
+    assert np.array_equal(ref, got)
+    proc = SegImageProcessor(1024, "panoptic")
+    a = proc.preprocess({"image_array": img})
+    b = proc.preprocess_device({"image_array": img}, device="cpu")
+    assert torch.equal(a["image_u8"], b["image_u8"]) and torch.equal(a["padding_mask"], b["padding_mask"])
+    assert (a["height"], a["width"]) == (b["height"], b["width"]) == (h, w)
