@@ -66,6 +66,49 @@ def pack_predictions(results, num_queries=100):
     return torch.stack(metas), (torch.stack(maps) if maps else None)
 
 
+def pack_mask_bits(masks):
+    """Instance masks [n, H, W] (float 0/1 or bool, as `Instances.pred_masks`) -> bit-packed uint8 [n, H, ceil(W/8)]
+    (MSB = leftmost pixel, numpy.packbits order): 1/32 of the bytes of the dense float masks of the reference API, the
+    form in which they cross NVLink / PCIe to the evaluators (RLE encoding stays on the host, pycocotools).  Torch ops
+    only: runs on the device that holds the masks."""
+    n, H, W = masks.shape
+    b = masks > 0 if masks.dtype != torch.bool else masks
+    pad = (-W) % 8
+    if pad:
+        b = torch.nn.functional.pad(b, (0, pad))
+    w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=masks.device)
+    return (b.view(n, H, -1, 8).to(torch.uint8) * w).sum(-1, dtype=torch.uint8)
+
+
+def unpack_mask_bits(bits, W):
+    """Inverse of `pack_mask_bits`: uint8 [n, H, ceil(W/8)] -> bool [n, H, W]."""
+    w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=bits.device)
+    return ((bits.unsqueeze(-1) & w) != 0).flatten(-2)[..., :W]
+
+
+def pack_instance_masks(results, num_queries=100):
+    """Bit-packed instance masks of a step for the prediction gather: uint8 [n_images, Q, H, ceil(W/8)] (zero padded to Q
+    slots; all images of a step share one output size)."""
+    out = []
+    for r in results:
+        m = r["instances"].pred_masks
+        bits = pack_mask_bits(m[:num_queries])
+        if bits.shape[0] < num_queries:
+            bits = torch.cat([bits, bits.new_zeros((num_queries - bits.shape[0],) + tuple(bits.shape[1:]))], 0)
+        out.append(bits)
+    return torch.stack(out)
+
+
+def gather_tensor(t):
+    """all_gather of one tensor along dim 0 (rank order); identity without a process group."""
+    if t is None or not (dist.is_initialized() and dist.get_world_size() > 1):
+        return t
+    t = t.contiguous()
+    g = torch.empty((dist.get_world_size() * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(g, t)
+    return g
+
+
 def gather_predictions(meta, maps):
     """all_gather of the per-step predictions: ([world*n, Q, 2], [world*n, H, W] or None), rank order."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):

@@ -41,6 +41,14 @@ def _worker(rank, world, port, out_q):
         res.append({"instances": inst, "panoptic_seg": (torch.full((4, 6), 7 * rank + i, dtype=torch.int32), [])})
     meta, maps = PD.pack_predictions(res, num_queries=5)
     gmeta, gmaps = PD.gather_predictions(meta, maps)
+    g = torch.Generator().manual_seed(rank)
+    for r_ in res:
+        r_["instances"].pred_masks = (torch.rand(3, 4, 6, generator=g) > 0.5).float()
+    bits = PD.pack_instance_masks(res, num_queries=5)                   # [2, 5, 4, 1] uint8
+    gbits = PD.gather_tensor(bits)
+    back = PD.unpack_mask_bits(gbits[2 * rank:2 * rank + 2], 6)
+    assert tuple(gbits.shape) == (4, 5, 4, 1) and all(
+        torch.equal(back[i, :3], res[i]["instances"].pred_masks > 0) and not back[i, 3:].any() for i in range(2))
     acc = PD.reduce_sum([torch.tensor([1.0, float(rank)]), torch.ones(2, 2, dtype=torch.int64)], "cpu")
     extra = (tuple(gmeta.shape), gmeta[:, 0, 1].tolist(), gmeta[:, 4, 1].tolist(), gmaps[:, 0, 0].tolist(),
              acc[0].tolist(), acc[1].sum().item())
@@ -74,3 +82,14 @@ def test_single_process_passthrough():
     x = torch.zeros(2, 10, 3)
     assert PD.gather_records(x) is x
     assert PD.max_over_ranks([3.0], "cpu") == [3.0]
+
+
+def test_mask_bit_packing_matches_numpy_packbits():
+    import numpy as np
+    g = torch.Generator().manual_seed(0)
+    for W in (8, 13, 64, 1021):
+        m = torch.rand(3, 5, W, generator=g) > 0.4
+        bits = PD.pack_mask_bits(m.float())
+        assert bits.dtype == torch.uint8 and tuple(bits.shape) == (3, 5, (W + 7) // 8)
+        assert np.array_equal(bits.numpy(), np.packbits(m.numpy(), axis=-1))
+        assert torch.equal(PD.unpack_mask_bits(bits, W), m)
